@@ -779,10 +779,30 @@ void co_index_stats(co_tree *t, const int *order, int n, float *means, float *va
     free(lv);
 }
 
+/* The sparse path product leaf = P @ node_scores (CobwebWrapper.py:241, 290): torch.sparse.mm
+ * on CPU accumulates each row's non-zeros in column order (root first) with a fused
+ * multiply-add in binary32 -- verified bit-for-bit against the reference's own node scores in
+ * tests/test_oracle_golden.py.  path_idx[l*maxlen + j] = node index or -1; path_w = w/len. */
+void co_leaf_scores(long nq, int nn, const float *node_scores, long nl, int maxlen, const int *path_idx,
+                    const float *path_w, float *leaf_scores) {
+#pragma omp parallel for schedule(static)
+    for (long q = 0; q < nq; q++) {
+        const float *s = node_scores + (size_t)q * nn;
+        for (long l = 0; l < nl; l++) {
+            float acc = 0.0f;
+            for (int j = 0; j < maxlen; j++) {
+                int b = path_idx[l * maxlen + j];
+                if (b < 0) break;
+                acc = fmaf(path_w[l * maxlen + j], s[b], acc);
+            }
+            leaf_scores[(size_t)q * nl + l] = acc;
+        }
+    }
+}
+
 /* cobweb_predict_indexed / cobweb_rank_scores node term (CobwebWrapper.py:230-236, 283-287):
  * s_n = -0.5 * (sum_d log V + sum_d (x - M)^2 / V) for every node, then the sparse path
- * product (:241): leaf = sum over the root->leaf path, in path order, of (w[depth]/len) * s.
- * path_idx[l*maxlen + j] = BFS node index or -1; path_w same shape (already w/len in fp32). */
+ * product (:241) via co_leaf_scores. */
 void co_dense_scores(int D, long nq, const float *Q, int nn, const float *means, const float *vars,
                      const float *sumlog, long nl, int maxlen, const int *path_idx, const float *path_w,
                      float *node_scores, float *leaf_scores) {
@@ -808,20 +828,7 @@ void co_dense_scores(int D, long nq, const float *Q, int nn, const float *means,
         free(tmp);
         free(tt.g);
     }
-    if (!leaf_scores) return;
-#pragma omp parallel for schedule(static)
-    for (long q = 0; q < nq; q++) {
-        const float *s = node_scores + (size_t)q * nn;
-        for (long l = 0; l < nl; l++) {
-            float acc = 0.0f;
-            for (int j = 0; j < maxlen; j++) {
-                int b = path_idx[l * maxlen + j];
-                if (b < 0) break;
-                acc = acc + path_w[l * maxlen + j] * s[b];
-            }
-            leaf_scores[(size_t)q * nl + l] = acc;
-        }
-    }
+    if (leaf_scores) co_leaf_scores(nq, nn, node_scores, nl, maxlen, path_idx, path_w, leaf_scores);
 }
 
 /* Throughput-oriented variant of the same scores for the CPU baseline (bench.py): plain

@@ -60,6 +60,7 @@ def lib():
         L.co_categorize.argtypes = [C.c_void_p, fp, C.c_long, C.c_int, C.c_long, C.c_int, C.c_int, ip, ip, ip, lp]
         L.co_index_stats.argtypes = [C.c_void_p, ip, C.c_int, fp, fp, fp]
         L.co_dense_scores.argtypes = [C.c_int, C.c_long, fp, C.c_int, fp, fp, fp, C.c_long, C.c_int, ip, fp, fp, fp]
+        L.co_leaf_scores.argtypes = [C.c_long, C.c_int, fp, C.c_long, C.c_int, ip, fp, fp]
         L.co_dense_scores_fast.argtypes = [C.c_int, C.c_long, fp, C.c_int, fp, fp, fp, fp]
         L.co_topk.argtypes = [fp, C.c_long, C.c_int, ip, fp]
         L.co_logf.restype = C.c_float
@@ -232,6 +233,17 @@ class OracleTree:
         lib().co_dense_scores(self.d, nq, _f(Q), nn, _f(ix["means"]), _f(ix["vars"]), _f(ix["sumlog"]), L,
                               ix["path_idx"].shape[1], _i(ix["path_idx"]), _f(ix["path_w"]), _f(ns), _f(ls))
         return ns, ls
+
+
+def leaf_scores(node_scores, path_idx, path_w):
+    """Sparse path product of the reference (sequential binary32 FMA, root first)."""
+    ns = _f32(np.atleast_2d(node_scores))
+    path_idx = np.ascontiguousarray(path_idx, np.int32)
+    path_w = _f32(path_w)
+    out = np.empty((ns.shape[0], path_idx.shape[0]), np.float32)
+    lib().co_leaf_scores(ns.shape[0], ns.shape[1], _f(ns), path_idx.shape[0], path_idx.shape[1], _i(path_idx),
+                         _f(path_w), _f(out))
+    return out
 
 
 def topk(scores, k):

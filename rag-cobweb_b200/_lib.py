@@ -1,0 +1,95 @@
+"""ctypes binding of libcobweb_b200.so (include/cobweb_b200.h).
+
+There is no CPU fallback: if the library is missing or CUDA is unavailable, every compute
+entry point raises.  Loading the library (symbol checks) works without a GPU.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "libcobweb_b200.so")
+
+CW_E_ARG, CW_E_CAPACITY, CW_E_CUDA, CW_E_FANOUT = -1, -2, -3, -4
+CW_USE_INFO, CW_USE_KL, CW_ACUITY_CUTOFF = 1, 2, 4
+(HDR_ROOT, HDR_N_USED, HDR_FREE_TOP, HDR_POOL_USED, HDR_STATUS, HDR_DONE, HDR_MAX_CHILD, HDR_N_SCORES, _h8, HDR_N_ROWS,
+ _h10, HDR_N_LEVELS, _h12) = range(13)
+HDR_WORDS = 16
+TILE_N, TILE_K, MAX_K, MAX_D, MAX_CHILDREN = 128, 16, 128, 4096, 2048
+IFIT_NODE_SLACK, IFIT_POOL_SLACK = 160, 16384
+
+EXPORTS = ["cw_version", "cw_last_error", "cw_store_init", "cw_ifit", "cw_categorize_ctas", "cw_categorize",
+           "cw_index_build", "cw_xt_floats", "cw_dense_node_scores", "cw_topk_chunks", "cw_dense_paths_topk",
+           "cw_predict_dense_host", "cw_ffma_peak"]
+
+
+class CwStore(C.Structure):
+    _fields_ = [("D", C.c_int32), ("cap", C.c_int32), ("pool_cap", C.c_int32), ("flags", C.c_int32),
+                ("prior_var", C.c_float), ("reserved", C.c_int32),
+                ("mean", C.c_void_p), ("m2", C.c_void_p), ("count", C.c_void_p), ("parent", C.c_void_p),
+                ("child_off", C.c_void_p), ("child_cnt", C.c_void_p), ("child_cap", C.c_void_p),
+                ("child_pool", C.c_void_p), ("n_sent", C.c_void_p), ("free_list", C.c_void_p), ("hdr", C.c_void_p)]
+
+
+class CwIndex(C.Structure):
+    _fields_ = [("D", C.c_int32), ("nn", C.c_int32), ("n_ntiles", C.c_int32), ("n_ktiles", C.c_int32),
+                ("R", C.c_void_p), ("MB", C.c_void_p), ("sumlog", C.c_void_p),
+                ("n_pos", C.c_int32), ("max_len", C.c_int32),
+                ("path_idx", C.c_void_p), ("path_w", C.c_void_p), ("pos_sid", C.c_void_p)]
+
+
+class CobwebB200Error(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library and declare prototypes.  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO):
+        raise CobwebB200Error(
+            f"{SO} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  There is no CPU fallback.")
+    L = C.CDLL(SO)
+    vp, i32, i64 = C.c_void_p, C.c_int, C.c_int64
+    L.cw_version.restype = C.c_int
+    L.cw_last_error.restype = C.c_char_p
+    L.cw_store_init.argtypes = [C.POINTER(CwStore), vp]
+    L.cw_ifit.argtypes = [C.POINTER(CwStore), vp, i64, vp, vp, vp, i64, i32, vp]
+    L.cw_categorize_ctas.restype = C.c_int
+    L.cw_categorize.argtypes = [C.POINTER(CwStore), vp, i64, i32, i64, i32, i32, i32, vp, i64, vp, vp, vp, vp, vp]
+    L.cw_index_build.argtypes = [C.POINTER(CwStore), vp, C.c_int32, C.POINTER(CwIndex), vp]
+    L.cw_xt_floats.restype = i64
+    L.cw_xt_floats.argtypes = [i64, C.c_int32]
+    L.cw_dense_node_scores.argtypes = [C.POINTER(CwIndex), vp, i64, vp, vp, i64, vp]
+    L.cw_topk_chunks.restype = i64
+    L.cw_topk_chunks.argtypes = [i64]
+    L.cw_dense_paths_topk.argtypes = [C.POINTER(CwIndex), vp, i64, i64, i32, vp, vp, vp, vp, vp]
+    L.cw_predict_dense_host.argtypes = [C.POINTER(CwIndex), vp, i64, i32, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp]
+    L.cw_ffma_peak.argtypes = [i32, i32, i32, vp, vp]
+    for name in EXPORTS:
+        getattr(L, name)  # AttributeError here = header and library out of sync
+    _lib = L
+    return L
+
+
+def check(rc, what=""):
+    if rc == 0:
+        return
+    msg = load().cw_last_error().decode(errors="replace")
+    raise CobwebB200Error(f"{what or 'libcobweb_b200'} failed with code {rc}: {msg}")
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise CobwebB200Error("cobweb-b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    load()
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,97 @@
+"""Host-side tree topology processing (pure numpy, runs anywhere).
+
+Inputs are the flat topology arrays of the node store (parent / child lists); outputs are the
+orderings and per-sentence root->leaf paths that CobwebWrapper.build_prediction_index
+(src/cobweb/CobwebWrapper.py:107-182) derives with a Python BFS over node objects.
+"""
+import numpy as np
+
+
+def bfs_order(root, child_off, child_cnt, child_pool):
+    """Nodes in BFS order, children in list order (the reference's index numbering,
+    CobwebWrapper.py:110-132).  Returns (order[nn] node ids, parent_b[nn] BFS index of the
+    parent or -1, depth[nn])."""
+    level = np.asarray([root], dtype=np.int64)
+    orders, parents, depths = [level], [np.asarray([-1], dtype=np.int64)], [np.zeros(1, np.int64)]
+    base, d = 0, 0
+    while True:
+        cnt = child_cnt[level].astype(np.int64)
+        tot = int(cnt.sum())
+        if tot == 0:
+            break
+        # gather the children of every node of this level, in order
+        par_local = np.repeat(np.arange(len(level), dtype=np.int64), cnt)
+        start = np.repeat(child_off[level].astype(np.int64), cnt)
+        within = np.arange(tot, dtype=np.int64) - np.repeat(np.cumsum(cnt) - cnt, cnt)
+        nxt = child_pool[start + within].astype(np.int64)
+        d += 1
+        orders.append(nxt)
+        parents.append(base + par_local)
+        depths.append(np.full(tot, d, np.int64))
+        base += len(level)
+        level = nxt
+    return np.concatenate(orders), np.concatenate(parents), np.concatenate(depths)
+
+
+def sentence_paths(order, parent_b, depth, leaf_of_sentence, level_weights=None, n_slots=None):
+    """Per-sentence root->leaf paths over index rows.
+
+    leaf_of_sentence[sid] = node id of the leaf holding sentence sid.  Sentences are laid out
+    in "positions" sorted by (index row of the leaf, sid) so neighbouring positions share
+    ancestors.  Returns dict(pos_sid[L], path_idx[max_len, L] (-1 padded), path_w[max_len, L]
+    with level_weights[j] / path_len in fp32, exactly the sparse values of
+    CobwebWrapper.py:160-169), max_len)."""
+    order = np.asarray(order, np.int64)
+    n_slots = int(order.max()) + 1 if n_slots is None else n_slots
+    row_of = np.full(n_slots, -1, np.int64)
+    row_of[order] = np.arange(len(order))
+    leaf_row = row_of[np.asarray(leaf_of_sentence, np.int64)]
+    if (leaf_row < 0).any():
+        raise ValueError("a sentence points at a node that is not in the tree")
+    L = len(leaf_row)
+    pos_sid = np.lexsort((np.arange(L), leaf_row)).astype(np.int32)
+    lr = leaf_row[pos_sid]
+    ldepth = depth[lr]
+    max_len = int(ldepth.max()) + 1 if L else 1
+    path_idx = np.full((max_len, L), -1, np.int32)
+    cur = lr.copy()
+    cols = np.arange(L)
+    for t in range(max_len):
+        j = ldepth - t
+        ok = j >= 0
+        path_idx[j[ok], cols[ok]] = cur[ok]
+        cur = np.where(ok, parent_b[np.maximum(cur, 0)], -1)
+    lw = [1.0] * 6 if level_weights is None else list(level_weights)
+    wrow = np.ones(max_len, np.float64)
+    wrow[: min(len(lw), max_len)] = lw[:max_len]
+    plen = (ldepth + 1).astype(np.float64)
+    path_w = (wrow[:, None] / plen[None, :]).astype(np.float32)
+    path_w[path_idx < 0] = 0.0
+    return dict(pos_sid=pos_sid, path_idx=path_idx, path_w=path_w, max_len=max_len)
+
+
+def generate_weight_schedule(schedule_type, max_depth, **kwargs):
+    """CobwebWrapper._generate_weight_schedule (CobwebWrapper.py:368-408)."""
+    if schedule_type == "constant":
+        return [kwargs.get("value", 1.0)] * max_depth
+    if schedule_type == "linear":
+        start, end = kwargs.get("start", 1.0), kwargs.get("end", 1.0)
+        if kwargs.get("direction", "increase") == "decrease":
+            start, end = end, start
+        if max_depth == 1:
+            return [start]
+        step = (end - start) / (max_depth - 1)
+        return [start + i * step for i in range(max_depth)]
+    if schedule_type == "quadratic":
+        start_n = kwargs.get("start_n", 1)
+        out = []
+        for i in range(max_depth):
+            n = start_n + i
+            if n == 0:
+                n = 1
+            out.append(1 / (n ** 2))
+        return out
+    if schedule_type == "exponential":
+        base = kwargs.get("base", 0.5)
+        return [base ** i for i in range(max_depth)]
+    raise ValueError(f"Unknown schedule type: {schedule_type}")

@@ -1,0 +1,370 @@
+"""CobwebWrapper with the reference's signatures (src/cobweb/CobwebWrapper.py), backed by the
+device node store and kernels.
+
+Reference surface kept: __init__(corpus, corpus_embeddings, encode_func) :13, add_sentences :52,
+build_prediction_index :91, cobweb_predict_indexed :210, cobweb_rank_scores :267,
+set_level_weights :335, set_weight_schedule :348, get_level_weights :410,
+get_weight_schedule_info :414, force_rebuild_index :422, cobweb_predict_fast :428,
+cobweb_predict :435, print_tree :463, dump_json :484, load_json :501, __len__ :557, attributes
+sentences / sentence_to_node / tree / device / max_init_search.  visualize_subtrees (graphviz
+rendering) is out of scope and raises NotImplementedError.
+Additive: predict_fast_batch / predict_batch / rank_scores_batch for query batches.
+
+Deliberate differences (DESIGN.md "Tie-breaking"): no 1e-6*randn noise and no in-leaf
+random.shuffle -- exact ties are broken by ascending sentence id.
+"""
+import ctypes as C
+import json
+
+import numpy as np
+import torch
+
+from . import _lib, topology
+from .tree import CobwebNode, CobwebTorchTree
+
+
+class DenseIndex:
+    """Device-resident prediction index (build_prediction_index, CobwebWrapper.py:91-208)."""
+
+    SCORE_BUDGET_BYTES = 2 << 30  # node-score scratch per query chunk
+
+    def __init__(self, tree, leaf_of_sentence, level_weights=None):
+        L = _lib.load()
+        self.tree = tree
+        dev = tree.device
+        t = tree.store.topology()
+        order, parent_b, depth = topology.bfs_order(t["root"], t["child_off"], t["child_cnt"], t["child_pool"])
+        self.order_host = order
+        self.nn = len(order)
+        self.max_depth = int(depth.max()) + 1
+        d = tree.d
+        self.n_ntiles = (self.nn + _lib.TILE_N - 1) // _lib.TILE_N
+        self.n_ktiles = (d + _lib.TILE_K - 1) // _lib.TILE_K
+        self.ld = self.n_ntiles * _lib.TILE_N
+        tile_elems = self.n_ntiles * self.n_ktiles * _lib.TILE_K * _lib.TILE_N
+        self.R = torch.empty(tile_elems, dtype=torch.float32, device=dev)
+        self.MB = torch.empty(tile_elems, dtype=torch.float32, device=dev)
+        self.sumlog = torch.zeros(self.ld, dtype=torch.float32, device=dev)
+        self.order = torch.as_tensor(order.astype(np.int32), device=dev)
+        self.n_pos = len(leaf_of_sentence)
+        ix = _lib.CwIndex()
+        ix.D, ix.nn, ix.n_ntiles, ix.n_ktiles = d, self.nn, self.n_ntiles, self.n_ktiles
+        ix.R, ix.MB, ix.sumlog = self.R.data_ptr(), self.MB.data_ptr(), self.sumlog.data_ptr()
+        if self.n_pos:
+            p = topology.sentence_paths(order, parent_b, depth, leaf_of_sentence, level_weights, n_slots=t["n_used"])
+            self.max_len = p["max_len"]
+            self.path_idx = torch.as_tensor(p["path_idx"], device=dev)
+            self.path_w = torch.as_tensor(p["path_w"], device=dev)
+            self.pos_sid = torch.as_tensor(p["pos_sid"], device=dev)
+            ix.n_pos, ix.max_len = self.n_pos, self.max_len
+            ix.path_idx, ix.path_w, ix.pos_sid = self.path_idx.data_ptr(), self.path_w.data_ptr(), self.pos_sid.data_ptr()
+        self.ix = ix
+        _lib.check(L.cw_index_build(tree.store.struct(), self.order.data_ptr(), self.nn, C.byref(ix), _lib.stream_ptr()),
+                   "cw_index_build")
+        self._ws = None
+
+    def bytes(self):
+        return (self.R.numel() + self.MB.numel() + self.sumlog.numel()) * 4
+
+    def chunk_queries(self):
+        return int(max(128, min(65535, self.SCORE_BUDGET_BYTES // (self.ld * 4)) // 128 * 128))
+
+    def workspace(self, nq, k):
+        """Device work buffers for chunks of up to nq queries and top-k up to k (grown on demand)."""
+        ws = self._ws
+        if ws and ws["cap_q"] >= nq and ws["cap_k"] >= k:
+            return ws
+        L, dev = _lib.load(), self.tree.device
+        nq = max(nq, ws["cap_q"]) if ws else nq
+        k = max(k, ws["cap_k"], 1) if ws else max(k, 1)
+        self._ws = ws = None
+        ws = dict(
+            cap_q=nq, cap_k=k,
+            q=torch.empty((nq, self.tree.d), dtype=torch.float32, device=dev),
+            xt=torch.empty(L.cw_xt_floats(nq, self.tree.d), dtype=torch.float32, device=dev),
+            scores=torch.empty((nq, self.ld), dtype=torch.float32, device=dev),
+            sid=torch.empty((nq, k), dtype=torch.int32, device=dev),
+            val=torch.empty((nq, k), dtype=torch.float32, device=dev),
+            scratch=torch.empty(max(1, nq * L.cw_topk_chunks(max(self.n_pos, 1)) * k * 2), dtype=torch.int32, device=dev),
+        )
+        self._ws = ws
+        return ws
+
+    def node_scores(self, Q):
+        """[nq, nn] node log-likelihood scores in index (BFS) order (CobwebWrapper.py:283-287)."""
+        L = _lib.load()
+        nq = Q.shape[0]
+        ws = self.workspace(nq, 0)
+        _lib.check(L.cw_dense_node_scores(C.byref(self.ix), Q.data_ptr(), nq, ws["xt"].data_ptr(), ws["scores"].data_ptr(),
+                                          self.ld, _lib.stream_ptr()), "cw_dense_node_scores")
+        return ws["scores"][:, : self.nn]
+
+    def predict(self, Q, k, want_leaf_scores=False):
+        """Device batch -> (sids [nq,k] int32, scores [nq,k], leaf_scores [nq,L] or None)."""
+        L = _lib.load()
+        nq_total = Q.shape[0]
+        step = self.chunk_queries()
+        sids = torch.empty((nq_total, max(k, 1)), dtype=torch.int32, device=Q.device)
+        vals = torch.empty((nq_total, max(k, 1)), dtype=torch.float32, device=Q.device)
+        leaf = torch.empty((nq_total, self.n_pos), dtype=torch.float32, device=Q.device) if want_leaf_scores else None
+        for lo in range(0, nq_total, step):
+            nq = min(step, nq_total - lo)
+            ws = self.workspace(min(step, nq_total), k)
+            q = Q[lo:lo + nq]
+            _lib.check(L.cw_dense_node_scores(C.byref(self.ix), q.data_ptr(), nq, ws["xt"].data_ptr(),
+                                              ws["scores"].data_ptr(), self.ld, _lib.stream_ptr()), "cw_dense_node_scores")
+            _lib.check(L.cw_dense_paths_topk(C.byref(self.ix), ws["scores"].data_ptr(), self.ld, nq, k,
+                                             leaf[lo:lo + nq].data_ptr() if leaf is not None else None,
+                                             sids[lo:lo + nq].data_ptr(), vals[lo:lo + nq].data_ptr(),
+                                             ws["scratch"].data_ptr(), _lib.stream_ptr()), "cw_dense_paths_topk")
+        return sids, vals, leaf
+
+    def predict_host(self, Q_host, k, out_sid=None, out_val=None):
+        """Host batch (numpy / pinned tensor) -> host ids/scores through the single C-ABI call
+        cw_predict_dense_host (H2D + kernels + D2H + sync inside)."""
+        L = _lib.load()
+        Qh = Q_host if torch.is_tensor(Q_host) else torch.from_numpy(np.ascontiguousarray(Q_host, np.float32))
+        nq_total = Qh.shape[0]
+        step = self.chunk_queries()
+        if out_sid is None:
+            out_sid = torch.empty((nq_total, k), dtype=torch.int32)
+            out_val = torch.empty((nq_total, k), dtype=torch.float32)
+        for lo in range(0, nq_total, step):
+            nq = min(step, nq_total - lo)
+            ws = self.workspace(min(step, nq_total), k)
+            _lib.check(L.cw_predict_dense_host(C.byref(self.ix), Qh[lo:lo + nq].data_ptr(), nq, k, ws["q"].data_ptr(),
+                                               ws["xt"].data_ptr(), ws["scores"].data_ptr(), self.ld, ws["sid"].data_ptr(),
+                                               ws["val"].data_ptr(), ws["scratch"].data_ptr(),
+                                               out_sid[lo:lo + nq].data_ptr(), out_val[lo:lo + nq].data_ptr(),
+                                               _lib.stream_ptr()), "cw_predict_dense_host")
+        return out_sid, out_val
+
+
+class CobwebWrapper:
+    def __init__(self, corpus=None, corpus_embeddings=None, encode_func=lambda x: x):
+        _lib.require_cuda()
+        self.encode_func = encode_func
+        self.sentences = []
+        self.device = "cuda"
+        self.max_init_search = 100000
+        self._index = None
+        self._level_weights = None
+        self._weight_schedule = None
+        self._schedule_params = {}
+        self.max_depth = 0
+        self._leaf_of_sentence = np.zeros(0, np.int32)
+
+        if corpus_embeddings is not None:
+            if isinstance(corpus_embeddings, list):
+                corpus_embeddings = torch.tensor(corpus_embeddings)
+            embedding_shape = corpus_embeddings.shape[1:]
+        elif corpus and len(corpus) > 0:
+            sample_emb = self.encode_func([corpus[0]])
+            embedding_shape = sample_emb.shape[1:]
+        else:
+            raise ValueError("CobwebWrapper needs a corpus or corpus_embeddings to size the tree")
+        self.tree = CobwebTorchTree(shape=embedding_shape, device=self.device)
+        if corpus_embeddings is not None:
+            if corpus is None:
+                corpus = [None] * len(corpus_embeddings)
+            self.add_sentences(corpus, corpus_embeddings)
+        elif corpus is not None and len(corpus) > 0:
+            self.add_sentences(corpus)
+
+    # ------------------------------------------------------------------ build
+    def add_sentences(self, new_sentences, new_vectors=None):
+        """CobwebWrapper.add_sentences (CobwebWrapper.py:52-80): one ifit per row, in order; the
+        leaf -> sentence-id bookkeeping is done by the kernel (n_sent) and the id map below."""
+        if new_vectors is None:
+            new_embeddings = self.encode_func(new_sentences)
+        else:
+            new_embeddings = new_vectors
+            if isinstance(new_embeddings, list):
+                new_embeddings = torch.tensor(new_embeddings)
+            if new_embeddings.shape[1] != self.tree.shape[0]:
+                print(f"[Warning] Provided vector dim {new_embeddings.shape[1]} != tree dim {self.tree.shape[0]}, re-encoding...")
+                new_embeddings = self.encode_func(new_sentences)
+        n = len(new_sentences)
+        X = self.tree._as_device_mat(new_embeddings)[:n]
+        leaves = self.tree.ifit_batch(X, tag_sentences=True)
+        self.sentences.extend(new_sentences)
+        self._leaf_of_sentence = np.concatenate([self._leaf_of_sentence, leaves.cpu().numpy()])
+        self.tree._sent = {}
+        self._invalidate_prediction_index()
+
+    @property
+    def sentence_to_node(self):
+        """sentence id -> concept handle (CobwebWrapper.py:77)."""
+        return {i: CobwebNode(self.tree, int(n)) for i, n in enumerate(self._leaf_of_sentence)}
+
+    def _sync_sentence_lists(self):
+        if self.tree._sent:
+            return
+        order = np.argsort(self._leaf_of_sentence, kind="stable")
+        for sid in order:
+            self.tree._sent.setdefault(int(self._leaf_of_sentence[sid]), []).append(int(sid))
+
+    def _invalidate_prediction_index(self):
+        self._index = None
+
+    @property
+    def _prediction_index_valid(self):
+        return self._index is not None
+
+    def build_prediction_index(self):
+        """CobwebWrapper.build_prediction_index (CobwebWrapper.py:91-208)."""
+        if self._index is not None:
+            return
+        self._index = DenseIndex(self.tree, self._leaf_of_sentence, self._level_weights)
+        self.max_depth = max(self.max_depth, self._index.max_depth)
+
+    def force_rebuild_index(self):
+        self._invalidate_prediction_index()
+        self.build_prediction_index()
+
+    # ------------------------------------------------------------------ level weights
+    def set_level_weights(self, weights):
+        self._level_weights = weights
+        self._weight_schedule = None
+        self._invalidate_prediction_index()
+
+    def set_weight_schedule(self, schedule_type, max_depth=10, **kwargs):
+        if self._prediction_index_valid:
+            max_depth = self.max_depth
+        self._weight_schedule = schedule_type
+        self._schedule_params = kwargs
+        self._level_weights = topology.generate_weight_schedule(schedule_type, max_depth, **kwargs)
+        self._invalidate_prediction_index()
+
+    def get_level_weights(self):
+        return self._level_weights if self._level_weights is not None else [1.0, 1.0, 1.0, 1.0]
+
+    def get_weight_schedule_info(self):
+        return {"schedule_type": self._weight_schedule, "schedule_params": self._schedule_params,
+                "current_weights": self.get_level_weights()}
+
+    def get_prediction_index_info(self):
+        ix = self._index
+        return {"index_valid": ix is not None, "total_nodes": ix.nn if ix else 0,
+                "leaf_paths_cached": ix.n_pos if ix else 0, "means_cached": ix is not None, "vars_cached": ix is not None}
+
+    # ------------------------------------------------------------------ dense predict
+    def _embed(self, input, is_embedding):
+        emb = input if is_embedding else self.encode_func([input])[0]
+        return self.tree._as_device_vec(emb).reshape(1, -1)
+
+    def predict_fast_batch(self, Q, k=5):
+        """Batched cobweb_predict_fast(return_ids=True): device tensors (ids [nq,k], scores [nq,k])."""
+        self.build_prediction_index()
+        Q = self.tree._as_device_mat(Q)
+        k = min(int(k), self._index.n_pos)
+        if k > _lib.MAX_K:
+            _, _, leaf = self._index.predict(Q, 0, want_leaf_scores=True)
+            vals, ids = torch.sort(leaf, dim=1, descending=True, stable=True)
+            return ids[:, :k].to(torch.int32), vals[:, :k]
+        sids, vals, _ = self._index.predict(Q, k)
+        return sids, vals
+
+    def rank_scores_batch(self, Q):
+        """Batched cobweb_rank_scores: [nq, L] leaf scores indexed by sentence id."""
+        self.build_prediction_index()
+        _, _, leaf = self._index.predict(self.tree._as_device_mat(Q), 0, want_leaf_scores=True)
+        return leaf
+
+    def cobweb_predict_indexed(self, input, k=5, return_ids=False, is_embedding=False):
+        """CobwebWrapper.cobweb_predict_indexed (CobwebWrapper.py:210-265), noise-free."""
+        self.build_prediction_index()
+        if len(self.sentences) == 0:
+            return []
+        ids, _ = self.predict_fast_batch(self._embed(input, is_embedding), k)
+        out = []
+        for sid in ids[0].cpu().tolist():
+            if 0 <= sid < len(self.sentences):
+                out.append(sid if return_ids else self.sentences[sid])
+        return out
+
+    def cobweb_predict_fast(self, input, k=5, return_ids=False, is_embedding=False):
+        return self.cobweb_predict_indexed(input, k, return_ids, is_embedding)
+
+    def cobweb_rank_scores(self, input, is_embedding=False):
+        """CobwebWrapper.cobweb_rank_scores (CobwebWrapper.py:267-294).  Forward only (autograd
+        w.r.t. the query is a SURVEY 8f 'next' row)."""
+        self.build_prediction_index()
+        if len(self.sentences) == 0:
+            return torch.empty(0, device=self.device)
+        x = input if is_embedding else self.encode_func([input])[0]
+        return self.rank_scores_batch(self.tree._as_device_vec(x).reshape(1, -1))[0]
+
+    # ------------------------------------------------------------------ best-first predict
+    def predict_batch(self, Q, k=5):
+        """Batched cobweb_predict: returns (leaves [nq,k] node ids on the host, nfound [nq],
+        lp_calls [nq])."""
+        r = self.tree.categorize_batch(Q, retrieve_k=k, use_best=True, max_nodes=self.max_init_search)
+        return r["leaves"].cpu().numpy(), r["nfound"].cpu().numpy(), r["lp_calls"].cpu().numpy()
+
+    def cobweb_predict(self, input, k=5, return_ids=False, is_embedding=False):
+        """CobwebWrapper.cobweb_predict (CobwebWrapper.py:435-461)."""
+        emb = input if is_embedding else self.encode_func([input])[0]
+        leaves = self.tree.categorize(emb, use_best=True, max_nodes=self.max_init_search, retrieve_k=k)
+        self._sync_sentence_lists()
+        results = []
+        for leaf in leaves:
+            for sid in sorted(self.tree._sent.get(leaf.node_id, [])):
+                if sid is None or sid >= len(self.sentences):
+                    continue
+                results.append(sid if return_ids else self.sentences[sid])
+        return results
+
+    # ------------------------------------------------------------------ misc
+    def print_tree(self):
+        self._sync_sentence_lists()
+        b = self.tree.bfs()
+        kids = [[] for _ in b["order"]]
+        for i in range(1, len(b["order"])):
+            kids[b["parent"][i]].append(i)
+
+        def rec(i, depth):
+            nid = int(b["order"][i])
+            print(f"{'  ' * depth}- Node ID {nid} Sentence ID: {list(self.tree._sent.get(nid, []))}")
+            for c in kids[i]:
+                rec(c, depth + 1)
+
+        print("\nCobweb Sentence Clustering Tree:")
+        rec(0, 0)
+
+    def dump_json(self, save_path=None):
+        """CobwebWrapper.dump_json (CobwebWrapper.py:484-497)."""
+        self._sync_sentence_lists()
+        state = {"tree": json.loads(self.tree.dump_json()), "sentences": self.sentences,
+                 "embedding_dim": self.tree.shape[0]}
+        if save_path:
+            with open(save_path, "w") as f:
+                json.dump(state, f, indent=2)
+        return json.dumps(state, indent=2)
+
+    @staticmethod
+    def load_json(json_data, encode_func=lambda x: x):
+        """CobwebWrapper.load_json (CobwebWrapper.py:500-555).  The reference's version crashes on
+        list-valued sentence ids; this one restores the id -> leaf map."""
+        data = json.loads(json_data) if isinstance(json_data, str) else json_data
+        w = CobwebWrapper.__new__(CobwebWrapper)
+        w.encode_func = encode_func
+        w.device = "cuda"
+        w.sentences = data.get("sentences", [])
+        w.max_init_search = data.get("max_init_search", 100000)
+        w._index, w._level_weights, w._weight_schedule, w._schedule_params, w.max_depth = None, None, None, {}, 0
+        w.tree = CobwebTorchTree(shape=(int(data["embedding_dim"]),), device=w.device)
+        w.tree.load_json(json.dumps(data["tree"]))
+        leaf = np.full(len(w.sentences), -1, np.int32)
+        for nid, lst in w.tree._sent.items():
+            for sid in lst:
+                if 0 <= sid < len(leaf):
+                    leaf[sid] = nid
+        w._leaf_of_sentence = leaf
+        return w
+
+    def visualize_subtrees(self, directory, num_leaves=6):
+        raise NotImplementedError("graphviz rendering is outside the hot-path scope (SURVEY.md section 2, row 3)")
+
+    def __len__(self):
+        return len(self.sentences)

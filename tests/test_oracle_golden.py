@@ -16,7 +16,7 @@ import os
 import numpy as np
 import pytest
 
-from oracle.cobweb_oracle import OracleTree, default_prior_var, lib
+from oracle.cobweb_oracle import OracleTree, default_prior_var, leaf_scores, lib
 from rag_cobweb_b200 import synth
 
 CASES = ["tiny_unit_64", "dups_unit_200x32", "unit_300x128", "whitened_600x256", "cfg1_unit_1000x384",
@@ -62,6 +62,8 @@ def check_queries(t, pos, g, q):
     ns, ls = t.dense_scores(q)
     np.testing.assert_allclose(ns, g["node_scores"], rtol=1e-5)  # whitened: torch fp32 sum of ~1e4-sized terms
     np.testing.assert_allclose(ls, g["rank_scores"], rtol=2e-6)
+    # the path product alone, fed the reference's own node scores, is bit-exact
+    assert np.array_equal(leaf_scores(g["node_scores"], t.index["path_idx"], t.index["path_w"]), g["rank_scores"])
     for i in range(len(q)):  # top-k ids of cobweb_predict_fast (noise-free)
         want = np.argsort(-g["rank_scores"][i], kind="stable")[:k]
         got = np.argsort(-ls[i], kind="stable")[:k]
