@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py -- batched Cobweb predict throughput on B200 (see DESIGN.md "Measurement").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl engine|reference] [--workload cfg3|cfg4|cfg2]
+
+A "step" is one pass of the hot path over one batch of synthetic queries: dense
+cobweb_predict_fast semantics (every query against every node, path product, top-k) on a tree
+built by the engine's own ifit from synthetic embeddings of the BASELINE.json shape.  One JSON
+line on stdout (rank 0).  Under torchrun the node store is built on rank 0 and broadcast over
+NCCL, each rank answers its own batch (weak scaling) and results are all-gathered inside the
+timed step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (docs, dim, queries per GPU, k, corpus kind, BASELINE.json config it is)
+    "cfg2": (1500, 1024, 300, 10, "unit", "configs[1] QQP-shape 1,500 docs x 1024-d, 300 queries"),
+    "cfg3": (100000, 768, 10000, 10, "unit", "configs[2] MS-MARCO-shape 100k passages x 768-d, 10k-query batch"),
+    "cfg4": (1000000, 1024, 16384, 10, "unit", "configs[3] 1M docs x 1024-d, query batches sharded over GPUs"),
+}
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for j, nm in enumerate(names) if any(len(r) >= 7 and r[3 + j].lower() == "active" for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback (B200_PROFILING.md)"
+
+
+def build_tree(args, docs, dim, kind):
+    """Setup (untimed): synthetic corpus -> engine ifit on the device.  Returns (wrapper, x, secs)."""
+    import torch
+    from rag_cobweb_b200 import CobwebWrapper, synth
+    x = synth.corpus(docs, dim, kind, seed=0)
+    torch.cuda.synchronize()
+    t0 = time.time()
+    w = CobwebWrapper(corpus=[None] * docs, corpus_embeddings=torch.from_numpy(x).cuda())
+    torch.cuda.synchronize()
+    return w, x, time.time() - t0
+
+
+def oracle_from_engine(w):
+    """Load the engine-built tree into the CPU oracle (setup for the CPU baseline legs)."""
+    from oracle.cobweb_oracle import OracleTree
+    b = w.tree.bfs()
+    mean, m2 = w.tree.store.rows(b["order"])
+    t = OracleTree(w.tree.d)
+    t.load(b["parent"], b["count"], b["nsent"], mean, m2)
+    pos = np.full(int(b["order"].max()) + 1, -1, np.int64)
+    pos[b["order"]] = np.arange(len(b["order"]))
+    t.leaf_of_sentence = pos[w._leaf_of_sentence].astype(np.int32)
+    t.n_sentences = len(t.leaf_of_sentence)
+    t.build_index()
+    return t
+
+
+def cpu_predict_rate(ot, q, k, min_seconds=3.0, max_rounds=50):
+    """queries/s of the oracle port's dense predict (all host threads OpenMP gives it)."""
+    from oracle.cobweb_oracle import leaf_scores, topk
+    done, t0 = 0, time.time()
+    while True:
+        ns, _ = ot.dense_scores(q, fast=True)
+        ls = leaf_scores(ns, ot.index["path_idx"], ot.index["path_w"])
+        for row in ls:
+            topk(row, k)
+        done += len(q)
+        if time.time() - t0 >= min_seconds or done >= max_rounds * len(q):
+            break
+    return done / (time.time() - t0)
+
+
+def run_reference(args, wl):
+    """--impl reference: the reference's CPU implementation of the path (oracle port, since the
+    Python reference cannot travel to this box) on the host cores, same config and metric."""
+    docs, dim, qn, k, kind, cfg = wl
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from rag_cobweb_b200 import synth
+    cores = os.cpu_count()
+    sample = 16
+    w, x, build_s = build_tree(args, docs, dim, kind)
+    ot = oracle_from_engine(w)
+    q, _ = synth.queries(x, sample, kind, seed=1)
+    for _ in range(max(args.warmup, 1)):
+        cpu_predict_rate(ot, q, k, min_seconds=0.0, max_rounds=1)
+    t0 = time.time()
+    for _ in range(args.steps):
+        cpu_predict_rate(ot, q, k, min_seconds=0.0, max_rounds=1)
+    dt = time.time() - t0
+    v = sample * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "cobweb_predict_fast queries/sec", "value": v, "unit": "queries/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": cfg, "docs": docs, "dim": dim, "k": k, "queries_per_step": sample,
+                   "tree": "built by the engine's ifit in setup, loaded into the CPU port"},
+        "cpu_baseline": {"value": v, "unit": "queries/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} queries per step against all {ot.index['means'].shape[0]} nodes, OpenMP"},
+        "e2e": {"value": v, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_engine(args, wl):
+    import torch
+    import torch.distributed as dist
+    from rag_cobweb_b200 import _lib, parallel, synth
+    docs, dim, qn, k, kind, cfg = wl
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    peaks, peak_src = measured_peaks()
+
+    # ---------------------------------------------------------------- setup (untimed)
+    if rank == 0:
+        w, x, build_s = build_tree(args, docs, dim, kind)
+        counters = w.tree.store.counters()
+        log(f"[bench] ifit {docs}x{dim}: {build_s:.1f}s = {docs / build_s:.0f} inserts/s")
+    else:
+        from rag_cobweb_b200 import CobwebWrapper
+        x = synth.corpus(docs, dim, kind, seed=0)
+        w = CobwebWrapper(corpus=[None], corpus_embeddings=torch.from_numpy(x[:1]).cuda())
+        build_s, counters = None, None
+    if world > 1:
+        t0 = time.time()
+        parallel.broadcast_store(w.tree, src=0)
+        leaf = torch.from_numpy(w._leaf_of_sentence if rank == 0 else np.zeros(docs, np.int32)).cuda()
+        dist.broadcast(leaf, 0)
+        w._leaf_of_sentence = leaf.cpu().numpy()
+        w.sentences = [None] * docs
+        w._invalidate_prediction_index()
+        torch.cuda.synchronize()
+        log(f"[bench] rank {rank}: store broadcast {time.time() - t0:.2f}s")
+    w.build_prediction_index()
+    ix = w._index
+    # this rank's batch: global batch = world * qn, contiguous shards
+    q_all, targets_all = synth.queries(x, qn * world, kind, seed=1, targets=np.arange(qn * world) % docs)
+    lo, hi = parallel.shard_bounds(qn * world, world, rank)
+    q_host = torch.from_numpy(q_all[lo:hi]).pin_memory()
+    q_dev = q_host.cuda()
+    out_sid_h = torch.empty((qn, k), dtype=torch.int32).pin_memory()
+    out_val_h = torch.empty((qn, k), dtype=torch.float32).pin_memory()
+    chunks = (qn + ix.chunk_queries() - 1) // ix.chunk_queries()
+    launches_per_step = 4 * chunks
+
+    def step_device():
+        ids, vals, _ = ix.predict(q_dev, k)
+        if world > 1:
+            ids, vals = parallel.gather_results(ids, vals)
+        return ids, vals
+
+    def step_host():
+        ix.predict_host(q_host, k, out_sid_h, out_val_h)
+        if world > 1:
+            parallel.gather_results(out_sid_h.cuda(non_blocking=True), out_val_h.cuda(non_blocking=True))
+
+    def timed(fn, steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+        step_host()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_dev = timed(step_device, args.steps)
+    ms_host = timed(step_host, args.steps)
+    # dominant kernel alone: the node-score kernel over one chunk of the batch, CUDA events on its stream
+    nq_k = min(qn, ix.chunk_queries())
+    ix.node_scores(q_dev[:nq_k])
+    ms_kernel = timed(lambda: ix.node_scores(q_dev[:nq_k]), max(args.steps, 5)) / max(args.steps, 5)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # FP32-FMA issue peak measured the same way (back-to-back FFMA chains, CUDA events, best of 5)
+    L = _lib.load()
+    sink = torch.zeros(4, device="cuda")
+    ffma = 0.0
+    for _ in range(5):
+        blocks, threads, iters = 148 * 8, 256, 8000
+        L.cw_ffma_peak(blocks, threads, 10, sink.data_ptr(), None)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        L.cw_ffma_peak(blocks, threads, iters, sink.data_ptr(), None)
+        e1.record()
+        torch.cuda.synchronize()
+        ffma = max(ffma, 2.0 * blocks * threads * iters * 64 / e0.elapsed_time(e1) / 1e9)
+
+    # correctness inside the bench: recall@k of the timed configuration (target among returned ids)
+    ids, _ = step_device()
+    got = ids.cpu().numpy()[lo:hi] if world > 1 else ids.cpu().numpy()
+    recall = float(np.mean([t in g for t, g in zip(targets_all[lo:hi], got)]))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------------------------------------------------------- CPU baseline (rank 0, N = 1 only)
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle.cobweb_oracle import OracleTree
+        cores = os.cpu_count()
+        ot = oracle_from_engine(w)
+        sample = 16
+        rate = cpu_predict_rate(ot, q_all[:sample], k, min_seconds=8.0)
+        o2 = OracleTree(dim)
+        n_ins = min(docs, 1500)
+        t0 = time.time()
+        o2.ifit(x[:n_ins])
+        ifit_rate = n_ins / (time.time() - t0)
+        cpu = {"value": rate, "unit": "queries/s", "cores": cores, "kind": "port",
+               "sample": f"{sample} queries x all {ix.nn} nodes per pass, repeated for >= 8 s, OpenMP over {cores} cores",
+               "ifit_inserts_per_s": ifit_rate, "ifit_sample": f"first {n_ins} inserts, 1 thread"}
+
+    nn, n_pos = ix.nn, ix.n_pos
+    flops = 4.0 * nq_k * nn * dim  # two FFMAs per (query, node, attribute)
+    alg_bytes = 8.0 * nn * dim + 4.0 * nn + 4.0 * nq_k * dim + 4.0 * nq_k * nn
+    achieved = flops / (ms_kernel * 1e-3) / 1e12
+    total_q = qn * world
+    line = {
+        "metric": "cobweb_predict_fast queries/sec", "value": total_q * args.steps / (ms_dev * 1e-3), "unit": "queries/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": cfg, "docs": docs, "dim": dim, "nodes": nn, "queries_per_gpu": qn, "k": k,
+                   "parallelism": f"replicated store, query-sharded x{world}" if world > 1 else "single GPU",
+                   "l2": "inputs exceed L2 (node matrices %.0f MB per pass)" % (8.0 * nn * dim / 1e6)},
+        "e2e": {"value": total_q * args.steps / (ms_host * 1e-3), "unit": "queries/s",
+                "h2d_bytes_per_step": int(qn * dim * 4), "d2h_bytes_per_step": int(qn * k * 8),
+                "api": "cw_predict_dense_host (C ABI, pinned host buffers)"},
+        "gpu_launches": launches_per_step * args.steps,
+        "roofline": {"bound": "fp32", "achieved": achieved, "peak": ffma, "unit": "TFLOP/s", "frac": achieved / ffma,
+                     "traffic": None, "kernel": "dense_score_kernel", "kernel_ms": ms_kernel,
+                     "flops_per_launch": flops, "peak_source": "FFMA issue peak measured in this run (cw_ffma_peak)",
+                     "hbm_frac": alg_bytes / (ms_kernel * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                     "hbm_peak_source": peak_src},
+        "cpu_baseline": cpu,
+        "clocks": clocks,
+        "recall_at_k": recall,
+        "ifit": {"inserts_per_s": docs / build_s, "seconds": build_s, "levels_per_insert": counters["levels"] / docs,
+                 "rows_per_insert": counters["rows"] / docs,
+                 "hbm_frac": (counters["rows"] + counters["levels"] + docs) * (8.0 * dim + 4) / build_s / 1e9 / peaks["hbm_gbs"]},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--docs", type=int)
+    ap.add_argument("--queries", type=int)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = list(WORKLOADS[args.workload])
+    if args.docs:
+        wl[0] = args.docs
+    if args.queries:
+        wl[2] = args.queries
+    import __graft_entry__
+    if int(os.environ.get("LOCAL_RANK", "0")) == 0:
+        __graft_entry__._load_build_module().build()
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_engine(args, wl)
+
+
+if __name__ == "__main__":
+    main()

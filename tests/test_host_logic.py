@@ -1,0 +1,193 @@
+"""CPU tests of the host-side logic: topology processing against the oracle's index, the JSON
+wire format, weight schedules, the C-ABI library's exported symbols, and the multi-process
+query-sharding plumbing (gloo, world_size 2)."""
+import ctypes
+import json
+import os
+import re
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.cobweb_oracle import OracleTree
+from rag_cobweb_b200 import _lib, parallel, serialize, synth, topology
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def oracle_tree(n=300, d=32, kind="unit"):
+    x = synth.corpus(n, d, kind, seed=0)
+    t = OracleTree(d)
+    leaves = t.ifit(x)
+    return x, t, leaves
+
+
+def flat_topology(t):
+    """Store-style arrays (child_off/cnt/pool) from an oracle tree, node id = BFS index."""
+    b = t.bfs()
+    n = len(b["order"])
+    cnt = b["nchild"].astype(np.int64)
+    off = np.cumsum(cnt) - cnt
+    pool = np.zeros(max(int(cnt.sum()), 1), np.int32)
+    fill = np.zeros(n, np.int64)
+    for i in range(1, n):
+        p = b["parent"][i]
+        pool[off[p] + fill[p]] = i
+        fill[p] += 1
+    return b, off.astype(np.int32), cnt.astype(np.int32), pool
+
+
+def test_bfs_and_paths_match_oracle_index():
+    x, t, leaves = oracle_tree()
+    b, off, cnt, pool = flat_topology(t)
+    order, parent_b, depth = topology.bfs_order(0, off, cnt, pool)
+    assert np.array_equal(order, np.arange(len(order)))
+    assert np.array_equal(parent_b, b["parent"]) and np.array_equal(depth, b["depth"])
+    ix = t.build_index(level_weights=[1.0, 0.5, 0.25])
+    pos = np.full(int(b["order"].max()) + 1, -1)
+    pos[b["order"]] = np.arange(len(b["order"]))
+    p = topology.sentence_paths(order, parent_b, depth, pos[leaves], [1.0, 0.5, 0.25])
+    # positions are a permutation of sentence ids, grouped by leaf in tree order
+    assert sorted(p["pos_sid"].tolist()) == list(range(len(leaves)))
+    assert (np.diff(pos[leaves][p["pos_sid"]]) >= 0).all()
+    # per sentence the path and the weights are the oracle's (build_prediction_index semantics)
+    assert np.array_equal(p["path_idx"].T[np.argsort(p["pos_sid"])], ix["path_idx"])
+    assert np.array_equal(p["path_w"].T[np.argsort(p["pos_sid"])], ix["path_w"])
+
+
+def test_sentence_paths_rejects_dangling_leaf():
+    x, t, leaves = oracle_tree(60, 8)
+    b, off, cnt, pool = flat_topology(t)
+    order, parent_b, depth = topology.bfs_order(0, off, cnt, pool)
+    with pytest.raises(ValueError):
+        topology.sentence_paths(order[:-1], parent_b[:-1], depth[:-1], [len(order) - 1], n_slots=len(order))
+
+
+def test_weight_schedules_match_reference_formulas():
+    g = topology.generate_weight_schedule
+    assert g("constant", 3, value=2.0) == [2.0, 2.0, 2.0]
+    assert g("linear", 3, start=1.0, end=3.0) == [1.0, 2.0, 3.0]
+    assert g("linear", 3, start=1.0, end=3.0, direction="decrease") == [3.0, 2.0, 1.0]
+    assert g("linear", 1, start=5.0) == [5.0]
+    assert g("quadratic", 3) == [1.0, 0.25, 1 / 9]
+    assert g("quadratic", 2, start_n=0) == [1.0, 1.0]
+    assert g("exponential", 3, base=0.5) == [1.0, 0.5, 0.25]
+    with pytest.raises(ValueError):
+        g("cubic", 3)
+
+
+def test_json_wire_format_roundtrip_and_reference_shape():
+    x, t, leaves = oracle_tree(120, 16)
+    b = t.bfs()
+    mean, m2 = t.rows(b["order"])
+    pos = np.full(int(b["order"].max()) + 1, -1)
+    pos[b["order"]] = np.arange(len(b["order"]))
+    sids = [[] for _ in b["order"]]
+    for sid, leaf in enumerate(leaves):
+        sids[pos[leaf]].append(sid)
+    params = dict(use_info=True, acuity_cutoff=False, use_kl=True, shape=[16], alpha=1e-8, prior_var=0.0585)
+    doc = serialize.dump_tree_json(params, b["parent"], b["count"], mean, m2, sids)
+    data = json.loads(doc)
+    # the reference's document shape (CobwebTorchTree.py:67-81, CobwebTorchNode.py:741-772)
+    assert set(data) == {"use_info", "acuity_cutoff", "use_kl", "shape", "alpha", "prior_var", "root"}
+    assert set(data["root"]) == {"count", "mean", "meanSq", "sentence_id", "children"}
+    assert len(data["root"]["children"]) == b["nchild"][0]
+    p2, parent2, count2, mean2, m22, sids2 = serialize.load_tree_json(doc)
+    assert p2 == params
+    assert np.array_equal(parent2, b["parent"]) and np.array_equal(count2, b["count"])
+    assert np.array_equal(mean2, mean) and np.array_equal(m22, m2)  # fp32 -> decimal -> fp32 is lossless
+    assert sids2 == sids
+
+
+def test_library_exports_every_declared_symbol():
+    """The C ABI loads without a GPU and exports every function include/cobweb_b200.h declares."""
+    hdr = open(os.path.join(ROOT, "include", "cobweb_b200.h")).read()
+    declared = set(re.findall(r"^\s*(?:int|int64_t|const char \*)\s*(cw_\w+)\(", hdr, flags=re.M))
+    assert declared == set(_lib.EXPORTS)
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.cw_version() == 100
+    assert ctypes.sizeof(_lib.CwStore) == 24 + 11 * 8
+    assert lib.cw_topk_chunks(4097) == 2 and lib.cw_xt_floats(129, 20) == 2 * 2 * 16 * 128
+
+
+def test_engine_refuses_to_run_without_cuda():
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from rag_cobweb_b200 import CobwebB200Error, CobwebTorchTree, CobwebWrapper
+    with pytest.raises(CobwebB200Error):
+        CobwebTorchTree((8,))
+    with pytest.raises(CobwebB200Error):
+        CobwebWrapper(corpus=[None], corpus_embeddings=np.zeros((1, 8), np.float32))
+
+
+def test_shard_bounds_cover_everything():
+    for n in (0, 1, 7, 10, 64):
+        for w in (1, 2, 3, 8):
+            spans = [parallel.shard_bounds(n, w, r) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+def test_merge_topk_orders_by_score_then_id():
+    ids = torch.tensor([[5, 2, -1, 9, 7, 1]], dtype=torch.int32)
+    vals = torch.tensor([[1.0, 3.0, 99.0, 3.0, 0.5, 3.0]])
+    i, v = parallel.merge_topk(ids, vals, 4)
+    assert i.tolist() == [[1, 2, 9, 5]] and v.tolist() == [[3.0, 3.0, 3.0, 1.0]]
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q, ret):
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        x, t, _ = oracle_tree(200, 16)
+        t.build_index()
+        qs, _ = synth.queries(x, q, "unit", seed=1)
+        k = 5
+
+        def local_predict(batch):  # stand-in for the per-GPU engine call
+            _, ls = t.dense_scores(batch)
+            ids = np.argsort(-ls, axis=1, kind="stable")[:, :k].astype(np.int32)
+            return torch.from_numpy(ids), torch.from_numpy(np.take_along_axis(ls, ids.astype(np.int64), 1))
+
+        # query-sharded mode: each rank answers its shard, one all-gather returns the batch
+        lo, hi = parallel.shard_bounds(q, world, rank)
+        ids, vals = local_predict(qs[lo:hi])
+        gi, gv = parallel.gather_results(ids, vals)
+        full_i, full_v = local_predict(qs)
+        ok1 = torch.equal(gi, full_i) and torch.equal(gv, full_v)
+        # store-sharded mode: each rank scores only its sentences, candidates merged after all-gather
+        _, ls = t.dense_scores(qs)
+        slo, shi = parallel.shard_bounds(ls.shape[1], world, rank)
+        part = ls[:, slo:shi]
+        pid = np.argsort(-part, axis=1, kind="stable")[:, :k]
+        cand_i = torch.from_numpy((pid + slo).astype(np.int32))
+        cand_v = torch.from_numpy(np.take_along_axis(part, pid, 1))
+        ci, cv = parallel.gather_candidates(cand_i, cand_v)
+        mi, mv = parallel.merge_topk(ci, cv, k)
+        ok2 = torch.equal(mi, full_i) and torch.equal(mv, full_v)
+        ret[rank] = (ok1, ok2)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_query_sharding_world_size_2_gloo():
+    import torch.multiprocessing as mp
+    world, q = 2, 11  # odd batch: shards of different size
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, q, ret), nprocs=world, join=True)
+    assert dict(ret) == {0: (True, True), 1: (True, True)}
