@@ -34,7 +34,7 @@ class CwIndex(C.Structure):
     _fields_ = [("D", C.c_int32), ("nn", C.c_int32), ("n_ntiles", C.c_int32), ("n_ktiles", C.c_int32),
                 ("R", C.c_void_p), ("MB", C.c_void_p), ("sumlog", C.c_void_p),
                 ("n_pos", C.c_int32), ("max_len", C.c_int32),
-                ("path_idx", C.c_void_p), ("path_w", C.c_void_p), ("pos_sid", C.c_void_p)]
+                ("path_idx", C.c_void_p), ("path_len", C.c_void_p), ("w_table", C.c_void_p), ("pos_sid", C.c_void_p)]
 
 
 class CobwebB200Error(RuntimeError):

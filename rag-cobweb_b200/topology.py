@@ -67,7 +67,13 @@ def sentence_paths(order, parent_b, depth, leaf_of_sentence, level_weights=None,
     plen = (ldepth + 1).astype(np.float64)
     path_w = (wrow[:, None] / plen[None, :]).astype(np.float32)
     path_w[path_idx < 0] = 0.0
-    return dict(pos_sid=pos_sid, path_idx=path_idx, path_w=path_w, max_len=max_len)
+    # the same values as a (len, depth) table: the kernel reads path_len per position instead of a
+    # weight per (depth, position)
+    w_table = np.zeros((max_len + 1, max_len), np.float32)
+    for ln in range(1, max_len + 1):
+        w_table[ln] = (wrow / float(ln)).astype(np.float32)
+    return dict(pos_sid=pos_sid, path_idx=path_idx, path_w=path_w, path_len=(ldepth + 1).astype(np.int32),
+                w_table=w_table, max_len=max_len)
 
 
 def generate_weight_schedule(schedule_type, max_depth, **kwargs):

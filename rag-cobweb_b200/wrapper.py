@@ -54,10 +54,12 @@ class DenseIndex:
             p = topology.sentence_paths(order, parent_b, depth, leaf_of_sentence, level_weights, n_slots=t["n_used"])
             self.max_len = p["max_len"]
             self.path_idx = torch.as_tensor(p["path_idx"], device=dev)
-            self.path_w = torch.as_tensor(p["path_w"], device=dev)
+            self.path_len = torch.as_tensor(p["path_len"], device=dev)
+            self.w_table = torch.as_tensor(p["w_table"], device=dev)
             self.pos_sid = torch.as_tensor(p["pos_sid"], device=dev)
             ix.n_pos, ix.max_len = self.n_pos, self.max_len
-            ix.path_idx, ix.path_w, ix.pos_sid = self.path_idx.data_ptr(), self.path_w.data_ptr(), self.pos_sid.data_ptr()
+            ix.path_idx, ix.path_len, ix.pos_sid = self.path_idx.data_ptr(), self.path_len.data_ptr(), self.pos_sid.data_ptr()
+            ix.w_table = self.w_table.data_ptr()
         self.ix = ix
         _lib.check(L.cw_index_build(tree.store.struct(), self.order.data_ptr(), self.nn, C.byref(ix), _lib.stream_ptr()),
                    "cw_index_build")

@@ -55,6 +55,10 @@ def test_bfs_and_paths_match_oracle_index():
     # per sentence the path and the weights are the oracle's (build_prediction_index semantics)
     assert np.array_equal(p["path_idx"].T[np.argsort(p["pos_sid"])], ix["path_idx"])
     assert np.array_equal(p["path_w"].T[np.argsort(p["pos_sid"])], ix["path_w"])
+    # the (len, depth) weight table the kernel uses holds exactly those values
+    for j in range(p["max_len"]):
+        ok = p["path_idx"][j] >= 0
+        assert np.array_equal(p["w_table"][p["path_len"][ok], j], p["path_w"][j][ok])
 
 
 def test_sentence_paths_rejects_dangling_leaf():
@@ -111,7 +115,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name)
     assert lib.cw_version() == 100
     assert ctypes.sizeof(_lib.CwStore) == 24 + 11 * 8
-    assert lib.cw_topk_chunks(4097) == 2 and lib.cw_xt_floats(129, 20) == 2 * 2 * 16 * 128
+    assert lib.cw_topk_chunks(2049) == 2 and lib.cw_xt_floats(129, 20) == 2 * 2 * 16 * 128
 
 
 def test_engine_refuses_to_run_without_cuda():
