@@ -14,10 +14,11 @@ CW_USE_INFO, CW_USE_KL, CW_ACUITY_CUTOFF = 1, 2, 4
 (HDR_ROOT, HDR_N_USED, HDR_FREE_TOP, HDR_POOL_USED, HDR_STATUS, HDR_DONE, HDR_MAX_CHILD, HDR_N_SCORES, _h8, HDR_N_ROWS,
  _h10, HDR_N_LEVELS, _h12) = range(13)
 HDR_WORDS = 16
+SCRATCH_WORDS = 16384
 TILE_N, TILE_K, MAX_K, MAX_D, MAX_CHILDREN = 128, 16, 128, 4096, 2048
 IFIT_NODE_SLACK, IFIT_POOL_SLACK = 160, 16384
 
-EXPORTS = ["cw_version", "cw_last_error", "cw_store_init", "cw_ifit", "cw_categorize_ctas", "cw_categorize",
+EXPORTS = ["cw_version", "cw_last_error", "cw_store_init", "cw_ifit", "cw_set_ifit_cluster", "cw_categorize_ctas", "cw_categorize",
            "cw_index_build", "cw_xt_floats", "cw_dense_node_scores", "cw_topk_chunks", "cw_dense_paths_topk",
            "cw_predict_dense_host", "cw_ffma_peak"]
 
@@ -27,7 +28,7 @@ class CwStore(C.Structure):
                 ("prior_var", C.c_float), ("reserved", C.c_int32),
                 ("mean", C.c_void_p), ("m2", C.c_void_p), ("count", C.c_void_p), ("parent", C.c_void_p),
                 ("child_off", C.c_void_p), ("child_cnt", C.c_void_p), ("child_cap", C.c_void_p),
-                ("child_pool", C.c_void_p), ("n_sent", C.c_void_p), ("free_list", C.c_void_p), ("hdr", C.c_void_p)]
+                ("child_pool", C.c_void_p), ("n_sent", C.c_void_p), ("free_list", C.c_void_p), ("hdr", C.c_void_p), ("scratch", C.c_void_p)]
 
 
 class CwIndex(C.Structure):
@@ -59,6 +60,7 @@ def load():
     L.cw_last_error.restype = C.c_char_p
     L.cw_store_init.argtypes = [C.POINTER(CwStore), vp]
     L.cw_ifit.argtypes = [C.POINTER(CwStore), vp, i64, vp, vp, vp, i64, i32, vp]
+    L.cw_set_ifit_cluster.argtypes = [i32]
     L.cw_categorize_ctas.restype = C.c_int
     L.cw_categorize.argtypes = [C.POINTER(CwStore), vp, i64, i32, i64, i32, i32, i32, vp, i64, vp, vp, vp, vp, vp]
     L.cw_index_build.argtypes = [C.POINTER(CwStore), vp, C.c_int32, C.POINTER(CwIndex), vp]

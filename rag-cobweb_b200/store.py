@@ -50,6 +50,7 @@ class NodeStore:
             new["child_pool"][: self.pool_cap] = self.child_pool
         else:
             self.hdr = torch.zeros(_lib.HDR_WORDS, dtype=torch.int32, device=dev)
+            self.scratch = torch.zeros(_lib.SCRATCH_WORDS, dtype=torch.int32, device=dev)
         for k, v in new.items():
             setattr(self, k, v)
         self.cap, self.pool_cap = cap, pool_cap
@@ -60,7 +61,7 @@ class NodeStore:
             s = _lib.CwStore()
             s.D, s.cap, s.pool_cap, s.flags, s.prior_var = self.d, self.cap, self.pool_cap, self.flags, self.prior_var
             for k in ("mean", "m2", "count", "parent", "child_off", "child_cnt", "child_cap", "child_pool", "n_sent",
-                      "free_list", "hdr"):
+                      "free_list", "hdr", "scratch"):
                 setattr(s, k, getattr(self, k).data_ptr())
             self._struct = s
         return C.byref(self._struct)
@@ -82,6 +83,13 @@ class NodeStore:
         h = self.header()
         return dict(scores=self._u64(h, _lib.HDR_N_SCORES), rows=self._u64(h, _lib.HDR_N_ROWS),
                     levels=self._u64(h, _lib.HDR_N_LEVELS))
+
+    def ifit_phase_cycles(self):
+        """Cycles the lead CTA spent per ifit phase since the store was created (cw_ifit.cu MARK())."""
+        base = 16 + 4 * _lib.MAX_CHILDREN + 1 + 3
+        w = self.scratch[base:base + 20].cpu().numpy().view(np.int64)
+        names = ["apply", "S1", "lists+slices", "phaseA", "S2", "decA", "phaseB", "S3", "decB", "-"]
+        return dict(zip(names, w.tolist()))
 
     @property
     def root(self):

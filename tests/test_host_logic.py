@@ -114,8 +114,8 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name)
     assert lib.cw_version() == 100
-    assert ctypes.sizeof(_lib.CwStore) == 24 + 11 * 8
-    assert lib.cw_topk_chunks(2049) == 2 and lib.cw_xt_floats(129, 20) == 2 * 2 * 16 * 128
+    assert ctypes.sizeof(_lib.CwStore) == 24 + 12 * 8
+    assert lib.cw_topk_chunks(1025) == 2 and lib.cw_xt_floats(129, 20) == 2 * 2 * 16 * 128
 
 
 def test_engine_refuses_to_run_without_cuda():

@@ -15,6 +15,7 @@ torch.cuda.synchronize()
 dt = time.time() - t0
 c = w.tree.store.counters()
 print(f"ifit {n}x{d} {kind}: {dt:.2f}s = {n/dt:.0f} inserts/s; levels/insert {c['levels']/n:.2f} rows/insert {c['rows']/n:.1f} scores/insert {c['scores']/n:.1f} us/level {dt/c['levels']*1e6:.2f}")
+ph = w.tree.store.ifit_phase_cycles(); tot=sum(ph.values()); print("ifit phases (% of lead-CTA cycles):", {k: round(100*v/tot,1) for k,v in ph.items()}, "cycles/level", round(tot/c["levels"]))
 b = w.tree.bfs(); print("nodes", len(b['order']), "depth", b['depth'].max(), "max children", b['nchild'].max(), "mean children", b['nchild'][b['nchild']>0].mean())
 t0=time.time(); w.build_prediction_index(); torch.cuda.synchronize(); print(f"index build {time.time()-t0:.2f}s nn={w._index.nn} max_len={w._index.max_len}")
 q,_ = synth.queries(x, nq, kind, 1); qd = torch.from_numpy(q).cuda()
