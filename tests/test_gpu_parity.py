@@ -83,6 +83,24 @@ def test_ifit_duplicates_and_single_calls():
     assert np.array_equal(pos[np.asarray(got)], rpos[rl])
 
 
+def test_ifit_cluster_sizes_agree():
+    """The thread-block-cluster size only changes who scores which child: results are identical."""
+    from rag_cobweb_b200 import _lib
+    L = _lib.load()
+    x, _, ref = build_pair(400, 384, "unit")
+    rl, rops, _ = ref.ifit(x, trace=True)
+    try:
+        for ncta in (1, 2, 4, 8):
+            _lib.check(L.cw_set_ifit_cluster(ncta))
+            tree = CobwebTorchTree((384,))
+            leaves, ops, _ = tree.ifit_batch(x, tag_sentences=True, trace=True)
+            assert np.array_equal(ops, rops), ncta
+            assert_same_tree(tree, ref, leaves.cpu().numpy(), rl)
+        assert L.cw_set_ifit_cluster(3) != 0
+    finally:
+        L.cw_set_ifit_cluster(0)
+
+
 def test_ifit_capacity_growth_midway():
     x, tree, ref = build_pair(3000, 64, "unit")
     tree.IFIT_CHUNK = 700  # several launches, several reallocations of the store
