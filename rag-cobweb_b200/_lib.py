@@ -19,7 +19,7 @@ TILE_N, TILE_K, MAX_K, MAX_D, MAX_CHILDREN = 128, 16, 128, 4096, 2048
 IFIT_NODE_SLACK, IFIT_POOL_SLACK = 160, 16384
 
 EXPORTS = ["cw_version", "cw_last_error", "cw_store_init", "cw_ifit", "cw_set_ifit_cluster", "cw_categorize_ctas", "cw_categorize",
-           "cw_index_build", "cw_xt_floats", "cw_dense_node_scores", "cw_topk_chunks", "cw_dense_paths_topk",
+           "cw_index_build", "cw_xt_floats", "cw_score_ldq", "cw_dense_node_scores", "cw_topk_chunks", "cw_dense_paths_topk",
            "cw_predict_dense_host", "cw_ffma_peak"]
 
 
@@ -35,7 +35,7 @@ class CwIndex(C.Structure):
     _fields_ = [("D", C.c_int32), ("nn", C.c_int32), ("n_ntiles", C.c_int32), ("n_ktiles", C.c_int32),
                 ("R", C.c_void_p), ("MB", C.c_void_p), ("sumlog", C.c_void_p),
                 ("n_pos", C.c_int32), ("max_len", C.c_int32),
-                ("path_idx", C.c_void_p), ("path_len", C.c_void_p), ("w_table", C.c_void_p), ("pos_sid", C.c_void_p)]
+                ("path_idx", C.c_void_p), ("w_table", C.c_void_p), ("pos_rec", C.c_void_p)]
 
 
 class CobwebB200Error(RuntimeError):
@@ -66,6 +66,8 @@ def load():
     L.cw_index_build.argtypes = [C.POINTER(CwStore), vp, C.c_int32, C.POINTER(CwIndex), vp]
     L.cw_xt_floats.restype = i64
     L.cw_xt_floats.argtypes = [i64, C.c_int32]
+    L.cw_score_ldq.restype = i64
+    L.cw_score_ldq.argtypes = [i64]
     L.cw_dense_node_scores.argtypes = [C.POINTER(CwIndex), vp, i64, vp, vp, i64, vp]
     L.cw_topk_chunks.restype = i64
     L.cw_topk_chunks.argtypes = [i64]

@@ -97,8 +97,7 @@ __device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
 // 128-byte line per half-warp (2 wavefronts instead of 4).
 __global__ void __launch_bounds__(SCORE_THREADS, 2)
 dense_score_kernel(const float *__restrict__ XT, const float *__restrict__ R, const float *__restrict__ MB,
-                   const float *__restrict__ sumlog, float *__restrict__ out, long long ld, long long nq,
-                   int n_ktiles) {
+                   const float *__restrict__ sumlog, float *__restrict__ out, long long ldq, int n_ktiles) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     ScoreStage *st = reinterpret_cast<ScoreStage *>(smem_raw);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + STAGES * sizeof(ScoreStage));
@@ -184,27 +183,29 @@ dense_score_kernel(const float *__restrict__ XT, const float *__restrict__ R, co
         }
     }
 
-    // epilogue: -0.5 * (sumlog + quad)   (CobwebWrapper.py:232-236)
+    // epilogue: -0.5 * (sumlog + quad)   (CobwebWrapper.py:232-236), written NODE-major:
+    // out[node * ldq + query], so the path kernel reads 32 queries of one node as one 128-byte line
     const int b0 = nt * TN + nb;
     const float4 sla = *reinterpret_cast<const float4 *>(sumlog + b0);
     const float4 slb = *reinterpret_cast<const float4 *>(sumlog + b0 + 32);
     const float sl[8] = {sla.x, sla.y, sla.z, sla.w, slb.x, slb.y, slb.z, slb.w};
+    float o[8][8];  // [query][node]
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-        const long long q = (long long)qt * TQ + qb + (i < 4 ? i : 16 + (i - 4));
-        if (q < nq) {
-            float o[8];
+    for (int i = 0; i < 8; i++)
 #pragma unroll
-            for (int p = 0; p < 4; p++) {
-                float lo, hi;
-                unpack2(acc[i][p], lo, hi);
-                o[2 * p] = -0.5f * (sl[2 * p] + lo);
-                o[2 * p + 1] = -0.5f * (sl[2 * p + 1] + hi);
-            }
-            float *row = out + q * ld + b0;
-            *reinterpret_cast<float4 *>(row) = make_float4(o[0], o[1], o[2], o[3]);
-            *reinterpret_cast<float4 *>(row + 32) = make_float4(o[4], o[5], o[6], o[7]);
+        for (int p = 0; p < 4; p++) {
+            float lo, hi;
+            unpack2(acc[i][p], lo, hi);
+            o[i][2 * p] = -0.5f * (sl[2 * p] + lo);
+            o[i][2 * p + 1] = -0.5f * (sl[2 * p + 1] + hi);
         }
+    float *col = out + (long long)qt * TQ + qb;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const long long b = b0 + (j < 4 ? j : 32 + (j - 4));
+        float *row = col + b * ldq;
+        *reinterpret_cast<float4 *>(row) = make_float4(o[0][j], o[1][j], o[2][j], o[3][j]);
+        *reinterpret_cast<float4 *>(row + 16) = make_float4(o[4][j], o[5][j], o[6][j], o[7][j]);
     }
 }
 
@@ -226,7 +227,7 @@ tile_queries_kernel(const float *__restrict__ Q, long long nq, int D, int n_ktil
 }
 
 // ------------------------------------------------------------------ path product + top-k
-constexpr int PT_THREADS = 256, PT_CHUNK = 1024, PT_QB = 8, PT_MAXLEN = 64;
+constexpr int PT_MAXLEN = 64, PT_SLOTS = CW_MAX_K / 32;
 
 // order: score desc, then sentence id asc; sid < 0 = empty
 __device__ __forceinline__ bool cand_better(float as, int ai, float bs, int bi) {
@@ -236,172 +237,200 @@ __device__ __forceinline__ bool cand_better(float as, int ai, float bs, int bi) 
     return ai < bi;
 }
 
-// One warp selects the k best of n (score, sid) candidates held in shared memory, in order.
-// k <= 64: single pass.  The running top-k is kept sorted across the warp (rank r lives in
-// lane r%32, slot r/32); each step tests 32 candidates against the current k-th best with one
-// ballot and inserts the few that beat it (expected k*ln(n/k) insertions in total).
-// k > 64: k rounds of arg-max + knock-out.
-__device__ __forceinline__ void warp_select_topk(float *cs, const int *ci, int n, int k, float *out_s, int *out_i) {
-    const int lane = threadIdx.x & 31;
+// grid (position chunks, groups of `wpb` query groups): warp = 32 queries (lane = query) x one
+// chunk of sentence positions.  Positions are in tree order, so consecutive paths share a
+// prefix (siblings differ only in the leaf); the index stores per position
+// {len, common prefix m with the previous position, leaf row, sentence id} in one 16-byte
+// record.  The FMA chain's partial sums are kept per level in a lane-private shared-memory
+// stack and a position recomputes only levels m..len-1 -- the same operations in the same order
+// as a full root-to-leaf chain (bit-equal to torch.sparse.mm on the reference's side).  Each
+// level is one coalesced 128-byte read of the node-major score matrix.  Every lane keeps its
+// query's sorted top-k in shared memory ([rank][lane]) behind a register threshold.
+__global__ void __launch_bounds__(256)
+paths_topk_kernel(const float *__restrict__ ST, unsigned ldq, long long nq, int n_pos, int max_len,
+                  const int *__restrict__ path_pm, const int4 *__restrict__ pos_rec,
+                  const float *__restrict__ w_table, int k, float *leaf_scores, float *cand_s, int *cand_i,
+                  int n_chunks, int chunk_len) {
+    extern __shared__ __align__(16) unsigned char pt_smem[];
+    float *wt = reinterpret_cast<float *>(pt_smem);  // [(max_len+1) * max_len]
+    const int wt_n = (max_len + 1) * max_len;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    float *Ls = wt + wt_n + (size_t)warp * k * 32;                                                // [32 lanes][k]
+    int *Li = reinterpret_cast<int *>(wt + wt_n + (size_t)wpb * k * 32) + (size_t)warp * k * 32;  // [32 lanes][k]
+    float *St = wt + wt_n + (size_t)2 * wpb * k * 32 + (size_t)warp * max_len * 32;               // [max_len][32]
+    for (int i = threadIdx.x; i < wt_n; i += blockDim.x) wt[i] = w_table[i];
     const float NEG_INF = -__int_as_float(0x7f800000);
-    if (k <= 64) {
-        float ls[2] = {NEG_INF, NEG_INF};  // sorted list, best first
-        int li[2] = {-1, -1};
-        const int last_lane = (k - 1) & 31, last_slot = (k - 1) >> 5;
-        for (int base = 0; base < n; base += 32) {
-            const int i = base + lane;
-            float v = NEG_INF;
-            int id = -1;
-            if (i < n) { v = cs[i]; id = ci[i]; }
-            // current k-th best (threshold)
-            const float ts = __shfl_sync(0xffffffffu, last_slot ? ls[1] : ls[0], last_lane);
-            const int ti = __shfl_sync(0xffffffffu, last_slot ? li[1] : li[0], last_lane);
-            unsigned m = __ballot_sync(0xffffffffu, cand_better(v, id, ts, ti));
-            while (m) {
-                const int src = __ffs(m) - 1;
-                m &= m - 1;
-                const float cv = __shfl_sync(0xffffffffu, v, src);
-                const int cid = __shfl_sync(0xffffffffu, id, src);
-                // rank of the candidate = number of list entries that beat it
-                const unsigned b0 = __ballot_sync(0xffffffffu, cand_better(ls[0], li[0], cv, cid));
-                const unsigned b1 = __ballot_sync(0xffffffffu, cand_better(ls[1], li[1], cv, cid));
-                const int pos = __popc(b0) + __popc(b1);
-                if (pos >= k) continue;  // an earlier insertion of this step raised the bar
-                // shift entries at rank >= pos down by one, slot 1 first (it takes lane 31 of slot 0)
-                const float up0s = __shfl_up_sync(0xffffffffu, ls[0], 1), up1s = __shfl_up_sync(0xffffffffu, ls[1], 1);
-                const int up0i = __shfl_up_sync(0xffffffffu, li[0], 1), up1i = __shfl_up_sync(0xffffffffu, li[1], 1);
-                const float carry_s = __shfl_sync(0xffffffffu, ls[0], 31);
-                const int carry_i = __shfl_sync(0xffffffffu, li[0], 31);
-                const int r0 = lane, r1 = 32 + lane;
-                if (r1 > pos) { ls[1] = lane == 0 ? carry_s : up1s; li[1] = lane == 0 ? carry_i : up1i; }
-                if (r1 == pos) { ls[1] = cv; li[1] = cid; }
-                if (r0 > pos) { ls[0] = up0s; li[0] = up0i; }
-                if (r0 == pos) { ls[0] = cv; li[0] = cid; }
+    for (int i = lane; i < 32 * k; i += 32) { Ls[i] = NEG_INF; Li[i] = -1; }
+    __syncthreads();
+    const long long g = (long long)blockIdx.y * wpb + warp;
+    if (g * 32 >= nq) return;
+    const long long q = g * 32 + lane;
+    const bool qvalid = q < nq;
+    const float *col = ST + (qvalid ? q : g * 32);
+    const int chunk = blockIdx.x;
+    const int p0 = chunk * chunk_len, p1 = min(n_pos, p0 + chunk_len);
+    float thr_s = NEG_INF;
+    int thr_i = -1;
+    // one position ahead: its record and its leaf-level score are in flight while the current
+    // position is processed (the leaf row is the one read that is new for almost every position)
+    const int4 *rec = pos_rec + p0;
+    int4 rc = rec[0];
+    float leaf_c = col[(size_t)(unsigned)rc.z * ldq];
+    for (int p = p0; p < p1; p++) {
+        int4 rn = rc;
+        float leaf_n = 0.0f;
+        ++rec;
+        if (p + 1 < p1) {
+            rn = rec[0];
+            leaf_n = col[(size_t)(unsigned)rn.z * ldq];
+        }
+        const int len = rc.x;
+        const int m = p == p0 ? 0 : rc.y;
+        const float *w = wt + len * max_len;
+        float acc = m > 0 ? St[(m - 1) * 32 + lane] : 0.0f;
+        for (int j = m; j < len - 1; j++) {  // rare: the parent (or higher) changed as well
+            const int b = path_pm[(size_t)p * max_len + j];
+            acc = __fmaf_rn(w[j], col[(size_t)(unsigned)b * ldq], acc);
+            St[j * 32 + lane] = acc;
+        }
+        if (m < len) {
+            acc = __fmaf_rn(w[len - 1], leaf_c, acc);
+            St[(len - 1) * 32 + lane] = acc;
+        }
+        const int sid = rc.w;
+        if (qvalid && leaf_scores) leaf_scores[q * n_pos + sid] = acc;
+        // top-k: lanes whose candidate beats their query's k-th best are served one at a time by
+        // the whole warp (lane r handles rank r of that query's list): no divergent shifting loops
+        unsigned need = __ballot_sync(0xffffffffu, k > 0 && qvalid && cand_better(acc, sid, thr_s, thr_i));
+        while (need) {
+            const int L = __ffs(need) - 1;
+            need &= need - 1;
+            const float cv = __shfl_sync(0xffffffffu, acc, L);
+            float *ls = Ls + L * k;
+            int *li = Li + L * k;
+            // ranks in passes of 32, all reads before any write
+            float es[PT_SLOTS];
+            int ei[PT_SLOTS];
+            int pos = 0;
+#pragma unroll
+            for (int t = 0; t < PT_SLOTS; t++) {
+                if (t * 32 < k) {  // uniform: only the passes this k needs
+                    const int r = t * 32 + lane;
+                    es[t] = NEG_INF; ei[t] = -1;
+                    if (r < k) { es[t] = ls[r]; ei[t] = li[r]; }
+                    pos += __popc(__ballot_sync(0xffffffffu, r < k && cand_better(es[t], ei[t], cv, sid)));
+                }
             }
+            __syncwarp();
+            float new_thr_s = cv;
+            int new_thr_i = sid;
+#pragma unroll
+            for (int t = 0; t < PT_SLOTS; t++) {
+                if (t * 32 >= k) continue;
+                const int r = t * 32 + lane;
+                if (r >= pos && r + 1 < k) { ls[r + 1] = es[t]; li[r + 1] = ei[t]; }
+                if (r == pos) { ls[r] = cv; li[r] = sid; }
+                // the new k-th best: the old rank k-2 unless the candidate itself landed on rank k-1
+                if (k >= 2 && ((k - 2) >> 5) == t) {
+                    const float ps = __shfl_sync(0xffffffffu, es[t], (k - 2) & 31);
+                    const int pi = __shfl_sync(0xffffffffu, ei[t], (k - 2) & 31);
+                    if (pos < k - 1) { new_thr_s = ps; new_thr_i = pi; }
+                }
+            }
+            if (lane == L) { thr_s = new_thr_s; thr_i = new_thr_i; }
+            __syncwarp();
         }
-        if (lane < k) { out_s[lane] = ls[0]; out_i[lane] = li[0]; }
-        if (32 + lane < k) { out_s[32 + lane] = ls[1]; out_i[32 + lane] = li[1]; }
-        __syncwarp();
-        return;
+        rc = rn;
+        leaf_c = leaf_n;
     }
-    for (int r = 0; r < k; r++) {
-        float bs = 0.f;
-        int bi = -1, bp = -1;
-        for (int i = lane; i < n; i += 32) {
-            const float v = cs[i];
-            const int id = (v == NEG_INF) ? -1 : ci[i];
-            if (cand_better(v, id, bs, bi)) { bs = v; bi = id; bp = i; }
-        }
-        for (int o = 16; o > 0; o >>= 1) {
-            const float os = __shfl_xor_sync(0xffffffffu, bs, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, o), op = __shfl_xor_sync(0xffffffffu, bp, o);
-            if (cand_better(os, oi, bs, bi)) { bs = os; bi = oi; bp = op; }
-        }
-        if (lane == 0) {
-            out_s[r] = bs;
-            out_i[r] = bi;
-            if (bp >= 0) cs[bp] = NEG_INF;  // knock out the winner (scores are finite)
-        }
-        __syncwarp();
+    if (k > 0 && qvalid) {
+        float *os = cand_s + (q * n_chunks + chunk) * k;
+        int *oi = cand_i + (q * n_chunks + chunk) * k;
+        for (int r = 0; r < k; r++) { os[r] = Ls[lane * k + r]; oi[r] = Li[lane * k + r]; }
     }
 }
 
-// grid (chunks, query blocks of PT_QB): leaf scores of one chunk of positions for PT_QB queries
-// (path indices are read once per block of queries), then warp q picks query q's k best.
-// leaf = sequential FMA over the path, root first, of w_table[len][j] * node score.
-__global__ void __launch_bounds__(PT_THREADS)
-paths_topk_kernel(const float *__restrict__ node_scores, long long ld, long long nq, int n_pos, int max_len,
-                  const int *__restrict__ path_idx, const int *__restrict__ path_len,
-                  const float *__restrict__ w_table, const int *__restrict__ pos_sid, int k, float *leaf_scores,
-                  float *cand_s, int *cand_i, int n_chunks) {
-    extern __shared__ __align__(16) unsigned char pt_smem[];
-    float *cs = reinterpret_cast<float *>(pt_smem);             // [PT_QB][PT_CHUNK]
-    int *ci = reinterpret_cast<int *>(cs + PT_QB * PT_CHUNK);   // [PT_CHUNK] sentence ids
-    float *wt = reinterpret_cast<float *>(ci + PT_CHUNK);       // [(max_len+1) * max_len]
-    float *os_ = wt + (PT_MAXLEN + 1) * PT_MAXLEN;              // [PT_QB][CW_MAX_K]
-    int *oi_ = reinterpret_cast<int *>(os_ + PT_QB * CW_MAX_K);
-
-    const int chunk = blockIdx.x;
-    const long long q0 = (long long)blockIdx.y * PT_QB;
-    const int nqb = (int)min((long long)PT_QB, nq - q0);
-    const int p0 = chunk * PT_CHUNK;
-    const int n = min(PT_CHUNK, n_pos - p0);
-    for (int i = threadIdx.x; i < (max_len + 1) * max_len; i += PT_THREADS) wt[i] = w_table[i];
-    __syncthreads();
-    const float *s0 = node_scores + q0 * ld;
-    for (int i = threadIdx.x; i < n; i += PT_THREADS) {
-        const int p = p0 + i;
-        const int len = path_len[p];
-        const float *w = wt + len * max_len;
-        float acc[PT_QB];
+// Running top-k of one warp, kept sorted across the lanes: rank r lives in lane r%32, slot r/32
+// (register arrays ls/li, fully unrolled).  Used to merge the per-chunk candidate lists.
+__device__ __forceinline__ void topk_init(float (&ls)[PT_SLOTS], int (&li)[PT_SLOTS]) {
 #pragma unroll
-        for (int q = 0; q < PT_QB; q++) acc[q] = 0.0f;
-        // 4 path levels at a time: all index loads, then all 32 gathers, then the FMA chains in
-        // path order (keeps ~32 independent loads in flight instead of one dependent pair)
-        for (int j0 = 0; j0 < len; j0 += 4) {
-            int b[4];
+    for (int s = 0; s < PT_SLOTS; s++) { ls[s] = -__int_as_float(0x7f800000); li[s] = -1; }
+}
+// Offer one candidate per lane (id < 0: none).  One ballot against the current k-th best; the
+// few candidates that beat it are inserted one by one.
+__device__ __forceinline__ void topk_offer(float (&ls)[PT_SLOTS], int (&li)[PT_SLOTS], int k, float v, int id) {
+    const int last_lane = (k - 1) & 31, last_slot = (k - 1) >> 5;
+    const int lane = threadIdx.x & 31;
+    float tsel = ls[0];
+    int isel = li[0];
 #pragma unroll
-            for (int u = 0; u < 4; u++) b[u] = (j0 + u < len) ? path_idx[(size_t)(j0 + u) * n_pos + p] : -1;
-            float sv[4][PT_QB];
+    for (int s = 1; s < PT_SLOTS; s++)
+        if (last_slot == s) { tsel = ls[s]; isel = li[s]; }
+    const float ts = __shfl_sync(0xffffffffu, tsel, last_lane);
+    const int ti = __shfl_sync(0xffffffffu, isel, last_lane);
+    unsigned m = __ballot_sync(0xffffffffu, cand_better(v, id, ts, ti));
+    while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        const float cv = __shfl_sync(0xffffffffu, v, src);
+        const int cid = __shfl_sync(0xffffffffu, id, src);
+        int pos = 0;  // rank of the candidate = number of list entries that beat it
 #pragma unroll
-            for (int u = 0; u < 4; u++)
+        for (int s = 0; s < PT_SLOTS; s++) pos += __popc(__ballot_sync(0xffffffffu, cand_better(ls[s], li[s], cv, cid)));
+        if (pos >= k) continue;  // an earlier insertion of this step raised the bar
+        float ups[PT_SLOTS], carry_s[PT_SLOTS];
+        int upi[PT_SLOTS], carry_i[PT_SLOTS];
 #pragma unroll
-                for (int q = 0; q < PT_QB; q++) sv[u][q] = (b[u] >= 0 && q < nqb) ? s0[(size_t)q * ld + b[u]] : 0.0f;
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                if (b[u] >= 0) {
-                    const float wj = w[j0 + u];
-#pragma unroll
-                    for (int q = 0; q < PT_QB; q++) acc[q] = __fmaf_rn(wj, sv[u][q], acc[q]);
-                }
-            }
+        for (int s = 0; s < PT_SLOTS; s++) {  // all reads of the old list first
+            ups[s] = __shfl_up_sync(0xffffffffu, ls[s], 1);
+            upi[s] = __shfl_up_sync(0xffffffffu, li[s], 1);
+            carry_s[s] = __shfl_sync(0xffffffffu, ls[s], 31);
+            carry_i[s] = __shfl_sync(0xffffffffu, li[s], 31);
         }
-        const int sid = pos_sid[p];
-        ci[i] = sid;
 #pragma unroll
-        for (int q = 0; q < PT_QB; q++) {
-            cs[q * PT_CHUNK + i] = acc[q];
-            if (leaf_scores && q < nqb) leaf_scores[(q0 + q) * n_pos + sid] = acc[q];
+        for (int s = 0; s < PT_SLOTS; s++) {  // shift ranks >= pos down by one, insert at pos
+            float ns = ups[s];
+            int ni = upi[s];
+            if (s > 0 && lane == 0) { ns = carry_s[s - 1]; ni = carry_i[s - 1]; }
+            const int r = s * 32 + lane;
+            if (r > pos) { ls[s] = ns; li[s] = ni; }
+            if (r == pos) { ls[s] = cv; li[s] = cid; }
         }
     }
-    __syncthreads();
-    if (k > 0) {
-        const int q = threadIdx.x >> 5;
-        if (q < nqb) {
-            warp_select_topk(cs + q * PT_CHUNK, ci, n, k, os_ + q * CW_MAX_K, oi_ + q * CW_MAX_K);
-            for (int r = threadIdx.x & 31; r < k; r += 32) {
-                cand_s[((q0 + q) * n_chunks + chunk) * k + r] = os_[q * CW_MAX_K + r];
-                cand_i[((q0 + q) * n_chunks + chunk) * k + r] = oi_[q * CW_MAX_K + r];
-            }
-        }
+}
+__device__ __forceinline__ void topk_store(const float (&ls)[PT_SLOTS], const int (&li)[PT_SLOTS], int k, float *out_s,
+                                           int *out_i) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int s = 0; s < PT_SLOTS; s++) {
+        const int r = s * 32 + lane;
+        if (r < k) { out_s[r] = ls[s]; out_i[r] = li[s]; }
     }
 }
 
 // grid (ceil(nq/8)): warp w merges the n_chunks*k candidates of one query into the final k
-__global__ void __launch_bounds__(PT_THREADS)
+__global__ void __launch_bounds__(256)
 merge_topk_kernel(const float *__restrict__ cand_s, const int *__restrict__ cand_i, long long nq, int n_chunks, int k,
                   int *out_sid, float *out_score) {
-    extern __shared__ __align__(16) unsigned char sm_raw[];
-    const int n = n_chunks * k;
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float *cs = reinterpret_cast<float *>(sm_raw) + (size_t)w * n;
-    int *ci = reinterpret_cast<int *>(reinterpret_cast<float *>(sm_raw) + (size_t)(PT_THREADS / 32) * n) + (size_t)w * n;
-    __shared__ float os_[PT_THREADS / 32][CW_MAX_K];
-    __shared__ int oi_[PT_THREADS / 32][CW_MAX_K];
-    const long long q = (long long)blockIdx.x * (PT_THREADS / 32) + w;
+    const long long q = (long long)blockIdx.x * 8 + w;
     if (q >= nq) return;
-    const float NEG_INF = -__int_as_float(0x7f800000);
-    for (int i = lane; i < n; i += 32) {
-        const int id = cand_i[q * n + i];
-        cs[i] = id >= 0 ? cand_s[q * n + i] : NEG_INF;
-        ci[i] = id;
+    const int n = n_chunks * k;
+    float ls[PT_SLOTS];
+    int li[PT_SLOTS];
+    topk_init(ls, li);
+    for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        float v = 0.0f;
+        int id = -1;
+        if (i < n) { v = cand_s[q * n + i]; id = cand_i[q * n + i]; }
+        topk_offer(ls, li, k, v, id);
     }
+    topk_store(ls, li, k, out_score + q * k, out_sid + q * k);
     __syncwarp();
-    warp_select_topk(cs, ci, n, k, os_[w], oi_[w]);
-    for (int r = lane; r < k; r += 32) {
-        out_sid[q * k + r] = oi_[w][r];
-        out_score[q * k + r] = oi_[w][r] >= 0 ? os_[w][r] : NEG_INF;
-    }
+    // empty ranks (fewer than k sentences) report -inf
+    for (int r = lane; r < k; r += 32)
+        if (out_sid[q * k + r] < 0) out_score[q * k + r] = -__int_as_float(0x7f800000);
 }
 
 }  // namespace cw
@@ -414,10 +443,12 @@ extern "C" int64_t cw_xt_floats(int64_t nq, int32_t D) {
     return ((nq + TQ - 1) / TQ) * (int64_t)((D + TK - 1) / TK) * TK * TQ;
 }
 
+extern "C" int64_t cw_score_ldq(int64_t nq) { return (nq + TQ - 1) / TQ * TQ; }
+
 extern "C" int cw_dense_node_scores(const cw_index *ix, const float *Q, int64_t nq, float *xt_scratch,
-                                    float *node_scores, int64_t ld, void *stream) {
-    if (!ix || !Q || !node_scores || !xt_scratch || nq < 0 || ld < (int64_t)ix->n_ntiles * TN || (ld & 3)) {
-        cw_set_error("cw_dense_node_scores: bad argument (ld must be >= n_ntiles*%d and a multiple of 4)", TN);
+                                    float *node_scores, int64_t ldq, void *stream) {
+    if (!ix || !Q || !node_scores || !xt_scratch || nq < 0 || ldq < cw_score_ldq(nq) || (ldq & 3)) {
+        cw_set_error("cw_dense_node_scores: bad argument (ldq must be >= cw_score_ldq(nq) and a multiple of 4)");
         return CW_E_ARG;
     }
     if (nq == 0) return 0;
@@ -434,71 +465,66 @@ extern "C" int cw_dense_node_scores(const cw_index *ix, const float *Q, int64_t 
     }
     tile_queries_kernel<<<dim3(n_qtiles, ix->n_ktiles), 256, 0, st>>>(Q, nq, ix->D, ix->n_ktiles, xt_scratch);
     dense_score_kernel<<<dim3(n_qtiles, ix->n_ntiles), SCORE_THREADS, score_smem_bytes(), st>>>(
-        xt_scratch, ix->R, ix->MB, ix->sumlog, node_scores, ld, nq, ix->n_ktiles);
+        xt_scratch, ix->R, ix->MB, ix->sumlog, node_scores, ldq, ix->n_ktiles);
     return cw_check_cuda(cudaGetLastError(), "cw_dense_node_scores");
 }
 
-extern "C" int64_t cw_topk_chunks(int64_t n_pos) { return (n_pos + PT_CHUNK - 1) / PT_CHUNK; }
+// Upper bound of position chunks per query (sizes the caller's candidate scratch); the launch
+// picks fewer, larger chunks when the batch alone fills the GPU.
+extern "C" int64_t cw_topk_chunks(int64_t n_pos) { return (n_pos + 1023) / 1024; }
 
-static size_t paths_smem_bytes() {
-    return (size_t)PT_QB * PT_CHUNK * 4 + (size_t)PT_CHUNK * 4 + (size_t)(PT_MAXLEN + 1) * PT_MAXLEN * 4 +
-           (size_t)PT_QB * CW_MAX_K * 8;
-}
-
-extern "C" int cw_dense_paths_topk(const cw_index *ix, const float *node_scores, int64_t ld, int64_t nq, int k,
+extern "C" int cw_dense_paths_topk(const cw_index *ix, const float *node_scores, int64_t ldq, int64_t nq, int k,
                                    float *leaf_scores, int32_t *out_sid, float *out_score, int32_t *scratch,
                                    void *stream) {
-    if (!ix || !node_scores || nq < 0 || k < 0 || k > CW_MAX_K || ix->n_pos < 1 || !ix->path_idx || !ix->path_len ||
-        !ix->w_table || !ix->pos_sid || ix->max_len < 1 || ix->max_len > PT_MAXLEN ||
+    if (!ix || !node_scores || nq < 0 || k < 0 || k > CW_MAX_K || ix->n_pos < 1 || !ix->path_idx || !ix->pos_rec ||
+        !ix->w_table || ix->max_len < 1 || ix->max_len > PT_MAXLEN || ldq < cw_score_ldq(nq) || ldq > 0x7fffffffLL ||
         (k > 0 && (!out_sid || !out_score || !scratch))) {
         cw_set_error("cw_dense_paths_topk: bad argument (k=%d max %d, max_len=%d max %d)", k, CW_MAX_K,
                      ix ? ix->max_len : -1, PT_MAXLEN);
         return CW_E_ARG;
     }
     if (nq == 0) return 0;
-    if (nq > 65535LL * PT_QB) {
-        cw_set_error("cw_dense_paths_topk: at most %d queries per call (got %lld)", 65535 * PT_QB, (long long)nq);
+    cudaStream_t st = (cudaStream_t)stream;
+    // warps per CTA: per-lane top-k lists take k*256 bytes of shared memory per warp
+    int wpb = k > 0 ? 65536 / (k * 256) : 8;
+    if (wpb > 8) wpb = 8;
+    if (wpb < 1) wpb = 1;
+    const long long groups = (nq + 31) / 32;
+    const long long gblocks = (groups + wpb - 1) / wpb;
+    if (gblocks > 65535) {
+        cw_set_error("cw_dense_paths_topk: too many queries per call (%lld)", (long long)nq);
         return CW_E_ARG;
     }
-    cudaStream_t st = (cudaStream_t)stream;
-    const int n_chunks = (int)cw_topk_chunks(ix->n_pos);
+    // aim for ~32 warps per SM (the kernel is issue-bound, and each chunk pays k ln(n/k) top-k
+    // insertions per query): few large chunks for big batches, many small ones for one query
+    long long want = (148 * 32 + groups - 1) / groups;
+    const long long max_chunks = cw_topk_chunks(ix->n_pos);
+    if (want > max_chunks) want = max_chunks;
+    if (want < 1) want = 1;
+    const int chunk_len = (int)((ix->n_pos + want - 1) / want);
+    const int n_chunks = (ix->n_pos + chunk_len - 1) / chunk_len;
     float *cand_s = reinterpret_cast<float *>(scratch);
     int *cand_i = scratch + (size_t)nq * n_chunks * (k > 0 ? k : 1);
-    static bool configured = false;
-    if (!configured) {
+    const size_t smem = ((size_t)(ix->max_len + 1) * ix->max_len + (size_t)2 * wpb * k * 32 +
+                         (size_t)wpb * ix->max_len * 32) * sizeof(float);
+    static size_t configured = 48 * 1024;
+    if (smem > configured) {
         int rc = cw_check_cuda(cudaFuncSetAttribute(paths_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                    (int)paths_smem_bytes()),
+                                                    (int)smem),
                                "cw_dense_paths_topk: smem attribute");
         if (rc) return rc;
-        configured = true;
+        configured = smem;
     }
-    const unsigned qblocks = (unsigned)((nq + PT_QB - 1) / PT_QB);
-    paths_topk_kernel<<<dim3(n_chunks, qblocks), PT_THREADS, paths_smem_bytes(), st>>>(
-        node_scores, ld, nq, ix->n_pos, ix->max_len, ix->path_idx, ix->path_len, ix->w_table, ix->pos_sid, k,
-        leaf_scores, cand_s, cand_i, n_chunks);
-    if (k > 0) {
-        const int wpb = PT_THREADS / 32;
-        size_t smem = (size_t)wpb * n_chunks * k * 8;
-        if (smem > 200 * 1024) {
-            cw_set_error("cw_dense_paths_topk: k=%d with %d position chunks needs %zu bytes of shared memory", k, n_chunks, smem);
-            return CW_E_ARG;
-        }
-        static size_t merge_configured = 48 * 1024;
-        if (smem > merge_configured) {
-            int rc = cw_check_cuda(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                        (int)smem),
-                                   "cw_dense_paths_topk: smem attribute");
-            if (rc) return rc;
-            merge_configured = smem;
-        }
-        merge_topk_kernel<<<(unsigned)((nq + wpb - 1) / wpb), PT_THREADS, smem, st>>>(cand_s, cand_i, nq, n_chunks, k,
-                                                                                    out_sid, out_score);
-    }
+    paths_topk_kernel<<<dim3(n_chunks, (unsigned)gblocks), wpb * 32, smem, st>>>(
+        node_scores, (unsigned)ldq, nq, ix->n_pos, ix->max_len, ix->path_idx, reinterpret_cast<const int4 *>(ix->pos_rec),
+        ix->w_table, k, leaf_scores, cand_s, cand_i, n_chunks, chunk_len);
+    if (k > 0)
+        merge_topk_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, st>>>(cand_s, cand_i, nq, n_chunks, k, out_sid, out_score);
     return cw_check_cuda(cudaGetLastError(), "cw_dense_paths_topk");
 }
 
 extern "C" int cw_predict_dense_host(const cw_index *ix, const float *Q_host, int64_t nq, int k, float *Q_dev,
-                                     float *xt_scratch, float *node_scores, int64_t ld, int32_t *out_sid_dev, float *out_score_dev,
+                                     float *xt_scratch, float *node_scores, int64_t ldq, int32_t *out_sid_dev, float *out_score_dev,
                                      int32_t *scratch, int32_t *out_sid_host, float *out_score_host, void *stream) {
     if (!ix || !Q_host || !Q_dev || !out_sid_host || !out_score_host || k < 1) {
         cw_set_error("cw_predict_dense_host: bad argument");
@@ -508,8 +534,8 @@ extern "C" int cw_predict_dense_host(const cw_index *ix, const float *Q_host, in
     int rc = cw_check_cuda(cudaMemcpyAsync(Q_dev, Q_host, (size_t)nq * ix->D * sizeof(float), cudaMemcpyHostToDevice, st),
                            "cw_predict_dense_host: H2D");
     if (rc) return rc;
-    if ((rc = cw_dense_node_scores(ix, Q_dev, nq, xt_scratch, node_scores, ld, stream))) return rc;
-    if ((rc = cw_dense_paths_topk(ix, node_scores, ld, nq, k, nullptr, out_sid_dev, out_score_dev, scratch, stream)))
+    if ((rc = cw_dense_node_scores(ix, Q_dev, nq, xt_scratch, node_scores, ldq, stream))) return rc;
+    if ((rc = cw_dense_paths_topk(ix, node_scores, ldq, nq, k, nullptr, out_sid_dev, out_score_dev, scratch, stream)))
         return rc;
     rc = cw_check_cuda(cudaMemcpyAsync(out_sid_host, out_sid_dev, (size_t)nq * k * sizeof(int32_t),
                                        cudaMemcpyDeviceToHost, st),

@@ -72,8 +72,16 @@ def sentence_paths(order, parent_b, depth, leaf_of_sentence, level_weights=None,
     w_table = np.zeros((max_len + 1, max_len), np.float32)
     for ln in range(1, max_len + 1):
         w_table[ln] = (wrow / float(ln)).astype(np.float32)
-    return dict(pos_sid=pos_sid, path_idx=path_idx, path_w=path_w, path_len=(ldepth + 1).astype(np.int32),
-                w_table=w_table, max_len=max_len)
+    # per-position record for the path kernel: {len, common prefix with the previous position, leaf row, sid}
+    plen_i = (ldepth + 1).astype(np.int64)
+    pfx = np.zeros(L, np.int64)
+    if L > 1:
+        same = (path_idx[:, 1:] == path_idx[:, :-1]) & (path_idx[:, 1:] >= 0)   # [max_len, L-1]
+        lead = np.cumprod(same, axis=0).sum(axis=0)                               # matching leading levels
+        pfx[1:] = np.where(plen_i[1:] == plen_i[:-1], np.minimum(lead, plen_i[1:]), 0)
+    pos_rec = np.stack([plen_i, pfx, lr, pos_sid.astype(np.int64)], axis=1).astype(np.int32)
+    return dict(pos_sid=pos_sid, path_idx=path_idx, path_w=path_w, path_len=plen_i.astype(np.int32),
+                w_table=w_table, pos_rec=np.ascontiguousarray(pos_rec), max_len=max_len)
 
 
 def generate_weight_schedule(schedule_type, max_depth, **kwargs):

@@ -26,7 +26,7 @@ from .tree import CobwebNode, CobwebTorchTree
 class DenseIndex:
     """Device-resident prediction index (build_prediction_index, CobwebWrapper.py:91-208)."""
 
-    SCORE_BUDGET_BYTES = 2 << 30  # node-score scratch per query chunk
+    SCORE_BUDGET_BYTES = 8 << 30  # node-score scratch per query chunk
 
     def __init__(self, tree, leaf_of_sentence, level_weights=None):
         L = _lib.load()
@@ -40,7 +40,7 @@ class DenseIndex:
         d = tree.d
         self.n_ntiles = (self.nn + _lib.TILE_N - 1) // _lib.TILE_N
         self.n_ktiles = (d + _lib.TILE_K - 1) // _lib.TILE_K
-        self.ld = self.n_ntiles * _lib.TILE_N
+        self.ld = self.n_ntiles * _lib.TILE_N  # rows of the node-major score matrix
         tile_elems = self.n_ntiles * self.n_ktiles * _lib.TILE_K * _lib.TILE_N
         self.R = torch.empty(tile_elems, dtype=torch.float32, device=dev)
         self.MB = torch.empty(tile_elems, dtype=torch.float32, device=dev)
@@ -53,13 +53,11 @@ class DenseIndex:
         if self.n_pos:
             p = topology.sentence_paths(order, parent_b, depth, leaf_of_sentence, level_weights, n_slots=t["n_used"])
             self.max_len = p["max_len"]
-            self.path_idx = torch.as_tensor(p["path_idx"], device=dev)
-            self.path_len = torch.as_tensor(p["path_len"], device=dev)
+            self.path_idx = torch.as_tensor(np.ascontiguousarray(p["path_idx"].T), device=dev)  # [n_pos, max_len]
             self.w_table = torch.as_tensor(p["w_table"], device=dev)
-            self.pos_sid = torch.as_tensor(p["pos_sid"], device=dev)
+            self.pos_rec = torch.as_tensor(p["pos_rec"], device=dev)  # [n_pos, 4]
             ix.n_pos, ix.max_len = self.n_pos, self.max_len
-            ix.path_idx, ix.path_len, ix.pos_sid = self.path_idx.data_ptr(), self.path_len.data_ptr(), self.pos_sid.data_ptr()
-            ix.w_table = self.w_table.data_ptr()
+            ix.path_idx, ix.pos_rec, ix.w_table = self.path_idx.data_ptr(), self.pos_rec.data_ptr(), self.w_table.data_ptr()
         self.ix = ix
         _lib.check(L.cw_index_build(tree.store.struct(), self.order.data_ptr(), self.nn, C.byref(ix), _lib.stream_ptr()),
                    "cw_index_build")
@@ -84,7 +82,8 @@ class DenseIndex:
             cap_q=nq, cap_k=k,
             q=torch.empty((nq, self.tree.d), dtype=torch.float32, device=dev),
             xt=torch.empty(L.cw_xt_floats(nq, self.tree.d), dtype=torch.float32, device=dev),
-            scores=torch.empty((nq, self.ld), dtype=torch.float32, device=dev),
+            ldq=int(L.cw_score_ldq(nq)),
+            scores=torch.empty((self.ld, int(L.cw_score_ldq(nq))), dtype=torch.float32, device=dev),  # node-major
             sid=torch.empty((nq, k), dtype=torch.int32, device=dev),
             val=torch.empty((nq, k), dtype=torch.float32, device=dev),
             scratch=torch.empty(max(1, nq * L.cw_topk_chunks(max(self.n_pos, 1)) * k * 2), dtype=torch.int32, device=dev),
@@ -98,8 +97,8 @@ class DenseIndex:
         nq = Q.shape[0]
         ws = self.workspace(nq, 0)
         _lib.check(L.cw_dense_node_scores(C.byref(self.ix), Q.data_ptr(), nq, ws["xt"].data_ptr(), ws["scores"].data_ptr(),
-                                          self.ld, _lib.stream_ptr()), "cw_dense_node_scores")
-        return ws["scores"][:, : self.nn]
+                                          ws["ldq"], _lib.stream_ptr()), "cw_dense_node_scores")
+        return ws["scores"][: self.nn, :nq].T
 
     def predict(self, Q, k, want_leaf_scores=False):
         """Device batch -> (sids [nq,k] int32, scores [nq,k], leaf_scores [nq,L] or None)."""
@@ -114,8 +113,8 @@ class DenseIndex:
             ws = self.workspace(min(step, nq_total), k)
             q = Q[lo:lo + nq]
             _lib.check(L.cw_dense_node_scores(C.byref(self.ix), q.data_ptr(), nq, ws["xt"].data_ptr(),
-                                              ws["scores"].data_ptr(), self.ld, _lib.stream_ptr()), "cw_dense_node_scores")
-            _lib.check(L.cw_dense_paths_topk(C.byref(self.ix), ws["scores"].data_ptr(), self.ld, nq, k,
+                                              ws["scores"].data_ptr(), ws["ldq"], _lib.stream_ptr()), "cw_dense_node_scores")
+            _lib.check(L.cw_dense_paths_topk(C.byref(self.ix), ws["scores"].data_ptr(), ws["ldq"], nq, k,
                                              leaf[lo:lo + nq].data_ptr() if leaf is not None else None,
                                              sids[lo:lo + nq].data_ptr(), vals[lo:lo + nq].data_ptr(),
                                              ws["scratch"].data_ptr(), _lib.stream_ptr()), "cw_dense_paths_topk")
@@ -135,7 +134,7 @@ class DenseIndex:
             nq = min(step, nq_total - lo)
             ws = self.workspace(min(step, nq_total), k)
             _lib.check(L.cw_predict_dense_host(C.byref(self.ix), Qh[lo:lo + nq].data_ptr(), nq, k, ws["q"].data_ptr(),
-                                               ws["xt"].data_ptr(), ws["scores"].data_ptr(), self.ld, ws["sid"].data_ptr(),
+                                               ws["xt"].data_ptr(), ws["scores"].data_ptr(), ws["ldq"], ws["sid"].data_ptr(),
                                                ws["val"].data_ptr(), ws["scratch"].data_ptr(),
                                                out_sid[lo:lo + nq].data_ptr(), out_val[lo:lo + nq].data_ptr(),
                                                _lib.stream_ptr()), "cw_predict_dense_host")

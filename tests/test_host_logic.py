@@ -55,6 +55,19 @@ def test_bfs_and_paths_match_oracle_index():
     # per sentence the path and the weights are the oracle's (build_prediction_index semantics)
     assert np.array_equal(p["path_idx"].T[np.argsort(p["pos_sid"])], ix["path_idx"])
     assert np.array_equal(p["path_w"].T[np.argsort(p["pos_sid"])], ix["path_w"])
+    # per-position records: length, shared prefix with the previous position, leaf row, sentence id
+    rec = p["pos_rec"]
+    assert np.array_equal(rec[:, 0], p["path_len"]) and np.array_equal(rec[:, 3], p["pos_sid"])
+    for i in range(len(rec)):
+        col = p["path_idx"][:, i]
+        assert rec[i, 2] == col[rec[i, 0] - 1]
+        if i:
+            prev = p["path_idx"][:, i - 1]
+            m = 0
+            while m < rec[i, 0] and rec[i, 0] == rec[i - 1, 0] and col[m] == prev[m]:
+                m += 1
+            assert rec[i, 1] == m
+    assert rec[0, 1] == 0 and (rec[1:, 1] >= rec[1:, 0] - 1).mean() > 0.5  # siblings share all but the leaf
     # the (len, depth) weight table the kernel uses holds exactly those values
     for j in range(p["max_len"]):
         ok = p["path_idx"][j] >= 0
