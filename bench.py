@@ -255,6 +255,13 @@ def run_engine(args, wl):
         torch.cuda.synchronize()
         ffma = max(ffma, 2.0 * blocks * threads * iters * 64 / e0.elapsed_time(e1) / 1e9)
 
+    # secondary: best-first predict (cobweb_predict semantics) on a slice of the batch
+    nbf = min(qn, 2048)
+    w.tree.categorize_batch(q_dev[:nbf], retrieve_k=k, max_nodes=w.max_init_search)
+    ms_bf = timed(lambda: w.tree.categorize_batch(q_dev[:nbf], retrieve_k=k, max_nodes=w.max_init_search), 3) / 3
+    bf = w.tree.categorize_batch(q_dev[:nbf], retrieve_k=k, max_nodes=w.max_init_search)
+    bf_rows = float(bf["lp_calls"].float().mean().item())
+
     # correctness inside the bench: recall@k of the timed configuration (target among returned ids)
     ids, _ = step_device()
     got = ids.cpu().numpy()[lo:hi] if world > 1 else ids.cpu().numpy()
@@ -306,6 +313,9 @@ def run_engine(args, wl):
         "cpu_baseline": cpu,
         "clocks": clocks,
         "recall_at_k": recall,
+        "best_first": {"queries_per_s": nbf * world / (ms_bf * 1e-3), "rows_scored_per_query": bf_rows,
+                       "queries": nbf, "hbm_frac": nbf * bf_rows * (8.0 * dim + 4) / (ms_bf * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                       "note": "cobweb_predict semantics (CobwebTorchTree._cobweb_categorize), algorithmic bytes = rows scored x (8D+4)"},
         "ifit": {"inserts_per_s": docs / build_s, "seconds": build_s, "levels_per_insert": counters["levels"] / docs,
                  "rows_per_insert": counters["rows"] / docs,
                  "hbm_frac": (counters["rows"] + counters["levels"] + docs) * (8.0 * dim + 4) / build_s / 1e9 / peaks["hbm_gbs"]},

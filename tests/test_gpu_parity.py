@@ -285,3 +285,42 @@ def test_properties_at_scale():
     pos = pos_of(b)
     assert np.array_equal(pos[r["leaves"].cpu().numpy()], rl)  # oracle slots == BFS index after load()
     assert np.array_equal(r["lp_calls"].cpu().numpy(), rc)
+
+
+def test_edge_cases_empty_and_tiny_trees():
+    """Empty tree, single-instance tree, k larger than the corpus, ragged batch sizes."""
+    d = 16
+    tree = CobwebTorchTree((d,))
+    x = synth.corpus(5, d, "unit", seed=3)
+    # categorize on an empty tree returns the (empty) root like the reference's loop does
+    assert tree.categorize(x[0]).node_id == tree.root.node_id
+    with pytest.raises(IndexError):
+        tree.categorize(x[0], retrieve_k=1)
+    leaf = tree.ifit(x[0])
+    assert leaf.node_id == tree.root.node_id and float(tree.root.count) == 1.0
+    assert np.array_equal(tree.root.mean.cpu().numpy(), x[0])
+    assert tree.root.children == [] and tree.root.parent is None
+    # a second, different instance fringe-splits the root
+    leaf2 = tree.ifit(x[1])
+    assert len(tree.root.children) == 2 and leaf2.parent == tree.root and float(tree.root.count) == 2.0
+    ref = OracleTree(d)
+    ref.ifit(x[:2], tag_sentences=False)
+    assert_same_tree(tree, ref)
+    # wrapper on a 3-document corpus: k beyond the corpus returns everything, best-first too
+    w = CobwebWrapper(corpus=["a", "b", "c"], corpus_embeddings=x[:3])
+    assert sorted(w.cobweb_predict_fast(x[0], k=10, return_ids=True, is_embedding=True)) == [0, 1, 2]
+    assert w.cobweb_predict_fast(x[1], k=1, is_embedding=True) == ["b"]
+    assert w.cobweb_predict(x[2], k=1, return_ids=True, is_embedding=True) == [2]
+    with pytest.raises(IndexError):
+        w.cobweb_predict(x[0], k=7, return_ids=True, is_embedding=True)
+    # ragged batches around the tile sizes of the dense path
+    n = 400
+    xs = synth.corpus(n, 40, "unit", seed=0)
+    w2 = CobwebWrapper(corpus=[None] * n, corpus_embeddings=xs)
+    q, _ = synth.queries(xs, 300, "unit", seed=1)
+    full = w2.predict_fast_batch(q, 7)[0].cpu().numpy()
+    for nq in (1, 31, 33, 127, 129, 257):
+        assert np.array_equal(w2.predict_fast_batch(q[:nq], 7)[0].cpu().numpy(), full[:nq])
+    # wrong dimension is rejected
+    with pytest.raises(ValueError):
+        w2.tree.ifit_batch(np.zeros((2, 41), np.float32))
