@@ -272,6 +272,24 @@ def run_engine(args, wl):
             dist.destroy_process_group()
         return
 
+    # ---------------------------------------------------------------- config 5 sample: streaming ifit (N = 1 only)
+    stream = None
+    if world == 1 and not args.no_cpu_baseline:
+        from rag_cobweb_b200 import CobwebTorchTree
+        n5 = 50000
+        x5 = torch.from_numpy(synth.corpus(n5, 256, "whitened", seed=0)).cuda()
+        t5 = CobwebTorchTree((256,))
+        torch.cuda.synchronize()
+        t0 = time.time()
+        t5.ifit_batch(x5, tag_sentences=True)
+        torch.cuda.synchronize()
+        dt5 = time.time() - t0
+        c5 = t5.store.counters()
+        stream = {"inserts_per_s": n5 / dt5, "sample": f"first {n5} inserts of configs[4] (whitened 256-d stream)",
+                  "levels_per_insert": c5["levels"] / n5, "rows_per_insert": c5["rows"] / n5,
+                  "us_per_level_step": dt5 / c5["levels"] * 1e6}
+        del t5, x5
+
     # ---------------------------------------------------------------- CPU baseline (rank 0, N = 1 only)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -285,9 +303,14 @@ def run_engine(args, wl):
         t0 = time.time()
         o2.ifit(x[:n_ins])
         ifit_rate = n_ins / (time.time() - t0)
+        o5 = OracleTree(256)
+        t0 = time.time()
+        o5.ifit(synth.corpus(1500, 256, "whitened", seed=0))
+        ifit5_rate = 1500 / (time.time() - t0)
         cpu = {"value": rate, "unit": "queries/s", "cores": cores, "kind": "port",
                "sample": f"{sample} queries x all {ix.nn} nodes per pass, repeated for >= 8 s, OpenMP over {cores} cores",
-               "ifit_inserts_per_s": ifit_rate, "ifit_sample": f"first {n_ins} inserts, 1 thread"}
+               "ifit_inserts_per_s": ifit_rate, "ifit_sample": f"first {n_ins} inserts, 1 thread",
+               "ifit_cfg5_inserts_per_s": ifit5_rate, "ifit_cfg5_sample": "first 1500 whitened 256-d inserts, 1 thread"}
 
     nn, n_pos = ix.nn, ix.n_pos
     flops = 4.0 * nq_k * nn * dim  # two FFMAs per (query, node, attribute)
@@ -316,6 +339,7 @@ def run_engine(args, wl):
         "best_first": {"queries_per_s": nbf * world / (ms_bf * 1e-3), "rows_scored_per_query": bf_rows,
                        "queries": nbf, "hbm_frac": nbf * bf_rows * (8.0 * dim + 4) / (ms_bf * 1e-3) / 1e9 / peaks["hbm_gbs"],
                        "note": "cobweb_predict semantics (CobwebTorchTree._cobweb_categorize), algorithmic bytes = rows scored x (8D+4)"},
+        "ifit_stream_cfg5": stream,
         "ifit": {"inserts_per_s": docs / build_s, "seconds": build_s, "levels_per_insert": counters["levels"] / docs,
                  "rows_per_insert": counters["rows"] / docs,
                  "hbm_frac": (counters["rows"] + counters["levels"] + docs) * (8.0 * dim + 4) / build_s / 1e9 / peaks["hbm_gbs"]},

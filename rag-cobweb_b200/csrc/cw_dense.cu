@@ -156,11 +156,11 @@ dense_score_kernel(const float *__restrict__ XT, const float *__restrict__ R, co
 #pragma unroll
             for (int i = 0; i < 8; i++) {
                 const uint64_t xx = pack2(xv[i], xv[i]);
+                uint64_t u[4];
 #pragma unroll
-                for (int p = 0; p < 4; p++) {
-                    const uint64_t u = ffma2(xx, r2[p], m2[p]);
-                    acc[i][p] = ffma2(u, u, acc[i][p]);
-                }
+                for (int p = 0; p < 4; p++) u[p] = ffma2(xx, r2[p], m2[p]);  // four independent FFMA2 ...
+#pragma unroll
+                for (int p = 0; p < 4; p++) acc[i][p] = ffma2(u[p], u[p], acc[i][p]);  // ... before their consumers
             }
         }
         // release the stage; the last warp to get here refills it
