@@ -313,6 +313,12 @@ def run_engine(args, wl):
                "ifit_cfg5_inserts_per_s": ifit5_rate, "ifit_cfg5_sample": "first 1500 whitened 256-d inserts, 1 thread"}
 
     nn, n_pos = ix.nn, ix.n_pos
+    traffic = None  # DRAM bytes of the dominant kernel per launch, from the committed ncu capture of this workload
+    tp = os.path.join(ROOT, "profiles", "traffic_cfg3.json")
+    if os.path.exists(tp):
+        tj = json.load(open(tp))
+        if tj["workload"] == {"docs": docs, "dim": dim, "queries": nq_k}:
+            traffic = tj["dense_score_kernel"]["dram_bytes_read"] + tj["dense_score_kernel"]["dram_bytes_write"]
     flops = 4.0 * nq_k * nn * dim  # two FFMAs per (query, node, attribute)
     alg_bytes = 8.0 * nn * dim + 4.0 * nn + 4.0 * nq_k * dim + 4.0 * nq_k * nn
     achieved = flops / (ms_kernel * 1e-3) / 1e12
@@ -329,7 +335,7 @@ def run_engine(args, wl):
                 "api": "cw_predict_dense_host (C ABI, pinned host buffers)"},
         "gpu_launches": launches_per_step * args.steps,
         "roofline": {"bound": "fp32", "achieved": achieved, "peak": ffma, "unit": "TFLOP/s", "frac": achieved / ffma,
-                     "traffic": None, "kernel": "dense_score_kernel", "kernel_ms": ms_kernel,
+                     "traffic": traffic, "algorithmic_bytes": alg_bytes, "kernel": "dense_score_kernel", "kernel_ms": ms_kernel,
                      "flops_per_launch": flops, "peak_source": "FFMA issue peak measured in this run (cw_ffma_peak)",
                      "hbm_frac": alg_bytes / (ms_kernel * 1e-3) / 1e9 / peaks["hbm_gbs"],
                      "hbm_peak_source": peak_src},
