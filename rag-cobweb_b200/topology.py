@@ -33,6 +33,25 @@ def bfs_order(root, child_off, child_cnt, child_pool):
     return np.concatenate(orders), np.concatenate(parents), np.concatenate(depths)
 
 
+def restrict_to_paths(order, parent_b, depth, leaves, n_slots):
+    """Keep only the index rows that lie on the root->leaf path of one of `leaves` (node ids).
+    Returns (order', parent_b', depth') in the same relative (BFS) order."""
+    order = np.asarray(order, np.int64)
+    row_of = np.full(n_slots, -1, np.int64)
+    row_of[order] = np.arange(len(order))
+    keep = np.zeros(len(order), bool)
+    cur = np.unique(row_of[np.asarray(leaves, np.int64)])
+    while len(cur):
+        cur = cur[~keep[cur]]
+        keep[cur] = True
+        cur = np.unique(parent_b[cur])
+        cur = cur[cur >= 0]
+    new_row = np.cumsum(keep) - 1
+    par = parent_b[keep]
+    par = np.where(par >= 0, new_row[np.maximum(par, 0)], -1)
+    return order[keep], par, depth[keep]
+
+
 def sentence_paths(order, parent_b, depth, leaf_of_sentence, level_weights=None, n_slots=None):
     """Per-sentence root->leaf paths over index rows.
 

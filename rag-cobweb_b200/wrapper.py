@@ -28,12 +28,21 @@ class DenseIndex:
 
     SCORE_BUDGET_BYTES = 8 << 30  # node-score scratch per query chunk
 
-    def __init__(self, tree, leaf_of_sentence, level_weights=None):
+    def __init__(self, tree, leaf_of_sentence, level_weights=None, sentence_ids=None):
+        """leaf_of_sentence[i] = leaf node id of sentence i.  sentence_ids (optional, sorted global
+        ids) restricts the index to a shard of the sentences: only the nodes on their root->leaf
+        paths are indexed and scored, returned ids stay global (store-sharded mode)."""
         L = _lib.load()
         self.tree = tree
         dev = tree.device
         t = tree.store.topology()
         order, parent_b, depth = topology.bfs_order(t["root"], t["child_off"], t["child_cnt"], t["child_pool"])
+        leaf_of_sentence = np.asarray(leaf_of_sentence)
+        self.sentence_ids = None
+        if sentence_ids is not None:
+            self.sentence_ids = np.asarray(sentence_ids, np.int64)
+            leaf_of_sentence = leaf_of_sentence[self.sentence_ids]
+            order, parent_b, depth = topology.restrict_to_paths(order, parent_b, depth, leaf_of_sentence, t["n_used"])
         self.order_host = order
         self.nn = len(order)
         self.max_depth = int(depth.max()) + 1
@@ -55,6 +64,8 @@ class DenseIndex:
             self.max_len = p["max_len"]
             self.path_idx = torch.as_tensor(np.ascontiguousarray(p["path_idx"].T), device=dev)  # [n_pos, max_len]
             self.w_table = torch.as_tensor(p["w_table"], device=dev)
+            if self.sentence_ids is not None:
+                p["pos_rec"][:, 3] = self.sentence_ids[p["pos_rec"][:, 3]]  # local position ids -> global ids
             self.pos_rec = torch.as_tensor(p["pos_rec"], device=dev)  # [n_pos, 4]
             ix.n_pos, ix.max_len = self.n_pos, self.max_len
             ix.path_idx, ix.pos_rec, ix.w_table = self.path_idx.data_ptr(), self.pos_rec.data_ptr(), self.w_table.data_ptr()
@@ -103,6 +114,8 @@ class DenseIndex:
     def predict(self, Q, k, want_leaf_scores=False):
         """Device batch -> (sids [nq,k] int32, scores [nq,k], leaf_scores [nq,L] or None)."""
         L = _lib.load()
+        if want_leaf_scores and self.sentence_ids is not None:
+            raise ValueError("leaf scores are indexed by global sentence id; not available on a sentence shard")
         nq_total = Q.shape[0]
         step = self.chunk_queries()
         sids = torch.empty((nq_total, max(k, 1)), dtype=torch.int32, device=Q.device)
@@ -207,6 +220,8 @@ class CobwebWrapper:
 
     def _invalidate_prediction_index(self):
         self._index = None
+        self._shard_key = None
+        self._shard_index = None
 
     @property
     def _prediction_index_valid(self):
@@ -265,6 +280,40 @@ class CobwebWrapper:
             return ids[:, :k].to(torch.int32), vals[:, :k]
         sids, vals, _ = self._index.predict(Q, k)
         return sids, vals
+
+    def predict_fast_sharded(self, Q, k=5, world=None, rank=None):
+        """Store-sharded dense predict (trees beyond one HBM): this rank indexes and
+        scores only its contiguous share of the sentences (in tree order) plus the nodes on their
+        paths, then per-rank top-k lists are all-gathered and merged.  Same ids and scores as
+        predict_fast_batch.  With world/rank given explicitly and no process group, returns this
+        shard's candidates (used by the single-GPU test that emulates the ranks one after another)."""
+        import torch.distributed as dist
+        from . import parallel
+        live = dist.is_available() and dist.is_initialized()
+        if world is None:
+            world, rank = (dist.get_world_size(), dist.get_rank()) if live else (1, 0)
+        key = (world, rank, len(self.sentences))
+        if getattr(self, "_shard_key", None) != key:
+            t = self.tree.store.topology()
+            order, parent_b, depth = topology.bfs_order(t["root"], t["child_off"], t["child_cnt"], t["child_pool"])
+            row_of = np.full(t["n_used"], -1, np.int64)
+            row_of[order] = np.arange(len(order))
+            tree_order = np.lexsort((np.arange(len(self._leaf_of_sentence)), row_of[self._leaf_of_sentence]))
+            lo, hi = parallel.shard_bounds(len(tree_order), world, rank)
+            self._shard_index = DenseIndex(self.tree, self._leaf_of_sentence, self._level_weights,
+                                           sentence_ids=np.sort(tree_order[lo:hi]))
+            self._shard_key = key
+        Q = self.tree._as_device_mat(Q)
+        kk = min(int(k), self._shard_index.n_pos, _lib.MAX_K)
+        ids, vals, _ = self._shard_index.predict(Q, kk)
+        if kk < k:  # pad so every rank contributes the same number of candidates
+            pad = k - kk
+            ids = torch.cat([ids, torch.full((ids.shape[0], pad), -1, dtype=ids.dtype, device=ids.device)], 1)
+            vals = torch.cat([vals, torch.full((vals.shape[0], pad), float("-inf"), device=vals.device)], 1)
+        if live and world > 1:
+            ci, cv = parallel.gather_candidates(ids, vals)
+            return parallel.merge_topk(ci, cv, k)
+        return ids, vals
 
     def rank_scores_batch(self, Q):
         """Batched cobweb_rank_scores: [nq, L] leaf scores indexed by sentence id."""

@@ -324,3 +324,26 @@ def test_edge_cases_empty_and_tiny_trees():
     # wrong dimension is rejected
     with pytest.raises(ValueError):
         w2.tree.ifit_batch(np.zeros((2, 41), np.float32))
+
+
+def test_store_sharded_predict_matches_full():
+    """every rank indexes only its share of the sentences and the nodes on their
+    paths; merged per-rank top-k == the single-index answer.  Ranks emulated one after another."""
+    from rag_cobweb_b200 import parallel
+    n, d, k = 1500, 96, 10
+    x = synth.corpus(n, d, "unit", seed=0)
+    x[700:720] = x[10:30]  # duplicates: several sentences per leaf
+    w = CobwebWrapper(corpus=[None] * n, corpus_embeddings=x)
+    q, _ = synth.queries(x, 100, "unit", seed=1)
+    full_i, full_v = w.predict_fast_batch(q, k)
+    for world in (2, 3):
+        parts = [w.predict_fast_sharded(q, k, world=world, rank=r) for r in range(world)]
+        nodes = []
+        for r in range(world):
+            w.predict_fast_sharded(q[:1], k, world=world, rank=r)
+            nodes.append(w._shard_index.nn)
+        assert max(nodes) < 0.8 * w._index.nn  # a shard really holds fewer nodes than the whole tree
+        ci = torch.cat([p[0] for p in parts], 1)
+        cv = torch.cat([p[1] for p in parts], 1)
+        mi, mv = parallel.merge_topk(ci, cv, k)
+        assert torch.equal(mi, full_i) and torch.equal(mv, full_v)

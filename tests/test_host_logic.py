@@ -74,6 +74,25 @@ def test_bfs_and_paths_match_oracle_index():
         assert np.array_equal(p["w_table"][p["path_len"][ok], j], p["path_w"][j][ok])
 
 
+def test_restrict_to_paths_keeps_exactly_the_ancestors():
+    x, t, leaves = oracle_tree(200, 8)
+    b, off, cnt, pool = flat_topology(t)
+    order, parent_b, depth = topology.bfs_order(0, off, cnt, pool)
+    pos = np.full(int(b["order"].max()) + 1, -1)
+    pos[b["order"]] = np.arange(len(b["order"]))
+    some = pos[leaves][::7]
+    o2, p2, d2 = topology.restrict_to_paths(order, parent_b, depth, some, len(order))
+    want = set()
+    for leaf in some:
+        nd = int(leaf)
+        while nd >= 0:
+            want.add(nd)
+            nd = int(parent_b[nd])
+    assert set(o2.tolist()) == want and list(o2) == sorted(want)
+    assert p2[0] == -1 and all(o2[p2[i]] == parent_b[o2[i]] for i in range(1, len(o2)))
+    assert np.array_equal(d2, depth[o2])
+
+
 def test_sentence_paths_rejects_dangling_leaf():
     x, t, leaves = oracle_tree(60, 8)
     b, off, cnt, pool = flat_topology(t)
