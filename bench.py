@@ -155,6 +155,20 @@ def run_reference(args, wl):
 
 
 def run_engine(args, wl):
+    # keep stdout clean for the single JSON line: libraries (NCCL's version banner) write to fd 1
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        line = _run_engine(args, wl)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def _run_engine(args, wl):
     import torch
     import torch.distributed as dist
     from rag_cobweb_b200 import _lib, parallel, synth
@@ -200,13 +214,26 @@ def run_engine(args, wl):
     chunks = (qn + ix.chunk_queries() - 1) // ix.chunk_queries()
     launches_per_step = 4 * chunks
 
+    store_mode = args.shard == "store" and world > 1
+    if store_mode:
+        # every rank answers the same global batch (the first qn queries) against its shard of the store
+        q_host = torch.from_numpy(q_all[:qn]).pin_memory()
+        q_dev = q_host.cuda()
+        lo, hi = 0, qn
+        w.predict_fast_sharded(q_dev[:8], k)  # builds this rank's shard index
+
     def step_device():
+        if store_mode:
+            return w.predict_fast_sharded(q_dev, k)
         ids, vals, _ = ix.predict(q_dev, k)
         if world > 1:
             ids, vals = parallel.gather_results(ids, vals)
         return ids, vals
 
     def step_host():
+        if store_mode:
+            w.predict_fast_sharded(q_host.cuda(non_blocking=True), k)[0].cpu()
+            return
         ix.predict_host(q_host, k, out_sid_h, out_val_h)
         if world > 1:
             parallel.gather_results(out_sid_h.cuda(non_blocking=True), out_val_h.cuda(non_blocking=True))
@@ -264,13 +291,13 @@ def run_engine(args, wl):
 
     # correctness inside the bench: recall@k of the timed configuration (target among returned ids)
     ids, _ = step_device()
-    got = ids.cpu().numpy()[lo:hi] if world > 1 else ids.cpu().numpy()
+    got = ids.cpu().numpy()[lo:hi] if (world > 1 and not store_mode) else ids.cpu().numpy()
     recall = float(np.mean([t in g for t, g in zip(targets_all[lo:hi], got)]))
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
-        return
+        return None
 
     # ---------------------------------------------------------------- config 5 sample: streaming ifit (N = 1 only)
     stream = None
@@ -322,13 +349,15 @@ def run_engine(args, wl):
     flops = 4.0 * nq_k * nn * dim  # two FFMAs per (query, node, attribute)
     alg_bytes = 8.0 * nn * dim + 4.0 * nn + 4.0 * nq_k * dim + 4.0 * nq_k * nn
     achieved = flops / (ms_kernel * 1e-3) / 1e12
-    total_q = qn * world
+    total_q = qn if store_mode else qn * world
     line = {
         "metric": "cobweb_predict_fast queries/sec", "value": total_q * args.steps / (ms_dev * 1e-3), "unit": "queries/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong" if store_mode else "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
         "config": {"workload": cfg, "docs": docs, "dim": dim, "nodes": nn, "queries_per_gpu": qn, "k": k,
-                   "parallelism": f"replicated store, query-sharded x{world}" if world > 1 else "single GPU",
+                   "parallelism": (f"store sharded x{world} (sentences + ancestor nodes), NCCL all-gather + top-k merge"
+                                   if store_mode else f"replicated store, query-sharded x{world}") if world > 1 else "single GPU",
                    "l2": "inputs exceed L2 (node matrices %.0f MB per pass)" % (8.0 * nn * dim / 1e6)},
         "e2e": {"value": total_q * args.steps / (ms_host * 1e-3), "unit": "queries/s",
                 "h2d_bytes_per_step": int(qn * dim * 4), "d2h_bytes_per_step": int(qn * k * 8),
@@ -350,9 +379,9 @@ def run_engine(args, wl):
                  "rows_per_insert": counters["rows"] / docs,
                  "hbm_frac": (counters["rows"] + counters["levels"] + docs) * (8.0 * dim + 4) / build_s / 1e9 / peaks["hbm_gbs"]},
     }
-    print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    return line
 
 
 def main():
@@ -365,6 +394,10 @@ def main():
     ap.add_argument("--docs", type=int)
     ap.add_argument("--queries", type=int)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard", default="query", choices=["query", "store"],
+                    help="N>1: 'query' replicates the store and shards the batch (weak scaling, default); "
+                         "'store' shards sentences+nodes, every rank answers the whole batch, per-rank top-k "
+                         "lists are merged after an NCCL all-gather (strong scaling)")
     args = ap.parse_args()
     wl = list(WORKLOADS[args.workload])
     if args.docs:
