@@ -10,7 +10,8 @@ device and the in-tree libcobweb_b200.so (there is no CPU fallback).
 from . import serialize, synth, topology  # noqa: F401
 from ._lib import CobwebB200Error  # noqa: F401
 from .tree import CobwebNode, CobwebTorchTree, default_prior_var  # noqa: F401
+from .whitening import PCAICAWhiteningModel  # noqa: F401
 from .wrapper import CobwebWrapper, DenseIndex  # noqa: F401
 
-__all__ = ["CobwebTorchTree", "CobwebWrapper", "CobwebNode", "DenseIndex", "CobwebB200Error", "default_prior_var",
+__all__ = ["CobwebTorchTree", "CobwebWrapper", "CobwebNode", "DenseIndex", "PCAICAWhiteningModel", "CobwebB200Error", "default_prior_var",
            "synth", "topology", "serialize"]

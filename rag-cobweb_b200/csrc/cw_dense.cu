@@ -227,7 +227,7 @@ tile_queries_kernel(const float *__restrict__ Q, long long nq, int D, int n_ktil
 }
 
 // ------------------------------------------------------------------ path product + top-k
-constexpr int PT_MAXLEN = 64, PT_SLOTS = CW_MAX_K / 32;
+constexpr int PT_MAXLEN = 1024, PT_SLOTS = CW_MAX_K / 32;
 
 // order: score desc, then sentence id asc; sid < 0 = empty
 __device__ __forceinline__ bool cand_better(float as, int ai, float bs, int bi) {
@@ -249,16 +249,19 @@ __device__ __forceinline__ bool cand_better(float as, int ai, float bs, int bi) 
 __global__ void __launch_bounds__(256)
 paths_topk_kernel(const float *__restrict__ ST, unsigned ldq, long long nq, int n_pos, int max_len,
                   const int *__restrict__ path_pm, const int4 *__restrict__ pos_rec,
-                  const float *__restrict__ w_table, int k, float *leaf_scores, float *cand_s, int *cand_i,
+                  const double *__restrict__ level_w, int k, float *leaf_scores, float *cand_s, int *cand_i,
                   int n_chunks, int chunk_len) {
     extern __shared__ __align__(16) unsigned char pt_smem[];
-    float *wt = reinterpret_cast<float *>(pt_smem);  // [(max_len+1) * max_len]
-    const int wt_n = (max_len + 1) * max_len;
+    // level weights in binary64; the path weight of level j on a path of length len is
+    // (float)(level_w[j] / len), the fp32 value the reference stores in its sparse path matrix
+    double *lw = reinterpret_cast<double *>(pt_smem);  // [max_len]
+    float *wt = reinterpret_cast<float *>(lw + max_len);
+    const int wt_n = 0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     float *Ls = wt + wt_n + (size_t)warp * k * 32;                                                // [32 lanes][k]
     int *Li = reinterpret_cast<int *>(wt + wt_n + (size_t)wpb * k * 32) + (size_t)warp * k * 32;  // [32 lanes][k]
     float *St = wt + wt_n + (size_t)2 * wpb * k * 32 + (size_t)warp * max_len * 32;               // [max_len][32]
-    for (int i = threadIdx.x; i < wt_n; i += blockDim.x) wt[i] = w_table[i];
+    for (int i = threadIdx.x; i < max_len; i += blockDim.x) lw[i] = level_w[i];
     const float NEG_INF = -__int_as_float(0x7f800000);
     for (int i = lane; i < 32 * k; i += 32) { Ls[i] = NEG_INF; Li[i] = -1; }
     __syncthreads();
@@ -286,15 +289,15 @@ paths_topk_kernel(const float *__restrict__ ST, unsigned ldq, long long nq, int 
         }
         const int len = rc.x;
         const int m = p == p0 ? 0 : rc.y;
-        const float *w = wt + len * max_len;
+        const double dlen = (double)len;
         float acc = m > 0 ? St[(m - 1) * 32 + lane] : 0.0f;
         for (int j = m; j < len - 1; j++) {  // rare: the parent (or higher) changed as well
             const int b = path_pm[(size_t)p * max_len + j];
-            acc = __fmaf_rn(w[j], col[(size_t)(unsigned)b * ldq], acc);
+            acc = __fmaf_rn((float)(lw[j] / dlen), col[(size_t)(unsigned)b * ldq], acc);
             St[j * 32 + lane] = acc;
         }
         if (m < len) {
-            acc = __fmaf_rn(w[len - 1], leaf_c, acc);
+            acc = __fmaf_rn((float)(lw[len - 1] / dlen), leaf_c, acc);
             St[(len - 1) * 32 + lane] = acc;
         }
         const int sid = rc.w;
@@ -477,7 +480,7 @@ extern "C" int cw_dense_paths_topk(const cw_index *ix, const float *node_scores,
                                    float *leaf_scores, int32_t *out_sid, float *out_score, int32_t *scratch,
                                    void *stream) {
     if (!ix || !node_scores || nq < 0 || k < 0 || k > CW_MAX_K || ix->n_pos < 1 || !ix->path_idx || !ix->pos_rec ||
-        !ix->w_table || ix->max_len < 1 || ix->max_len > PT_MAXLEN || ldq < cw_score_ldq(nq) || ldq > 0x7fffffffLL ||
+        !ix->level_w || ix->max_len < 1 || ix->max_len > PT_MAXLEN || ldq < cw_score_ldq(nq) || ldq > 0x7fffffffLL ||
         (k > 0 && (!out_sid || !out_score || !scratch))) {
         cw_set_error("cw_dense_paths_topk: bad argument (k=%d max %d, max_len=%d max %d)", k, CW_MAX_K,
                      ix ? ix->max_len : -1, PT_MAXLEN);
@@ -485,8 +488,10 @@ extern "C" int cw_dense_paths_topk(const cw_index *ix, const float *node_scores,
     }
     if (nq == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    // warps per CTA: per-lane top-k lists take k*256 bytes of shared memory per warp
-    int wpb = k > 0 ? 65536 / (k * 256) : 8;
+    // warps per CTA: per warp the per-lane top-k lists take k*256 bytes of shared memory and the
+    // partial-sum stack max_len*128 bytes
+    const size_t per_warp = (size_t)k * 256 + (size_t)ix->max_len * 128;
+    int wpb = (int)(98304 / per_warp);
     if (wpb > 8) wpb = 8;
     if (wpb < 1) wpb = 1;
     const long long groups = (nq + 31) / 32;
@@ -505,8 +510,7 @@ extern "C" int cw_dense_paths_topk(const cw_index *ix, const float *node_scores,
     const int n_chunks = (ix->n_pos + chunk_len - 1) / chunk_len;
     float *cand_s = reinterpret_cast<float *>(scratch);
     int *cand_i = scratch + (size_t)nq * n_chunks * (k > 0 ? k : 1);
-    const size_t smem = ((size_t)(ix->max_len + 1) * ix->max_len + (size_t)2 * wpb * k * 32 +
-                         (size_t)wpb * ix->max_len * 32) * sizeof(float);
+    const size_t smem = (size_t)ix->max_len * sizeof(double) + (size_t)wpb * per_warp;
     static size_t configured = 48 * 1024;
     if (smem > configured) {
         int rc = cw_check_cuda(cudaFuncSetAttribute(paths_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -517,7 +521,7 @@ extern "C" int cw_dense_paths_topk(const cw_index *ix, const float *node_scores,
     }
     paths_topk_kernel<<<dim3(n_chunks, (unsigned)gblocks), wpb * 32, smem, st>>>(
         node_scores, (unsigned)ldq, nq, ix->n_pos, ix->max_len, ix->path_idx, reinterpret_cast<const int4 *>(ix->pos_rec),
-        ix->w_table, k, leaf_scores, cand_s, cand_i, n_chunks, chunk_len);
+        ix->level_w, k, leaf_scores, cand_s, cand_i, n_chunks, chunk_len);
     if (k > 0)
         merge_topk_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, st>>>(cand_s, cand_i, nq, n_chunks, k, out_sid, out_score);
     return cw_check_cuda(cudaGetLastError(), "cw_dense_paths_topk");

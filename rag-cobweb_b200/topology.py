@@ -100,7 +100,7 @@ def sentence_paths(order, parent_b, depth, leaf_of_sentence, level_weights=None,
         pfx[1:] = np.where(plen_i[1:] == plen_i[:-1], np.minimum(lead, plen_i[1:]), 0)
     pos_rec = np.stack([plen_i, pfx, lr, pos_sid.astype(np.int64)], axis=1).astype(np.int32)
     return dict(pos_sid=pos_sid, path_idx=path_idx, path_w=path_w, path_len=plen_i.astype(np.int32),
-                w_table=w_table, pos_rec=np.ascontiguousarray(pos_rec), max_len=max_len)
+                w_table=w_table, level_w=wrow.copy(), pos_rec=np.ascontiguousarray(pos_rec), max_len=max_len)
 
 
 def generate_weight_schedule(schedule_type, max_depth, **kwargs):

@@ -63,12 +63,12 @@ class DenseIndex:
             p = topology.sentence_paths(order, parent_b, depth, leaf_of_sentence, level_weights, n_slots=t["n_used"])
             self.max_len = p["max_len"]
             self.path_idx = torch.as_tensor(np.ascontiguousarray(p["path_idx"].T), device=dev)  # [n_pos, max_len]
-            self.w_table = torch.as_tensor(p["w_table"], device=dev)
+            self.level_w = torch.as_tensor(p["level_w"], dtype=torch.float64, device=dev)
             if self.sentence_ids is not None:
                 p["pos_rec"][:, 3] = self.sentence_ids[p["pos_rec"][:, 3]]  # local position ids -> global ids
             self.pos_rec = torch.as_tensor(p["pos_rec"], device=dev)  # [n_pos, 4]
             ix.n_pos, ix.max_len = self.n_pos, self.max_len
-            ix.path_idx, ix.pos_rec, ix.w_table = self.path_idx.data_ptr(), self.pos_rec.data_ptr(), self.w_table.data_ptr()
+            ix.path_idx, ix.pos_rec, ix.level_w = self.path_idx.data_ptr(), self.pos_rec.data_ptr(), self.level_w.data_ptr()
         self.ix = ix
         _lib.check(L.cw_index_build(tree.store.struct(), self.order.data_ptr(), self.nn, C.byref(ix), _lib.stream_ptr()),
                    "cw_index_build")

@@ -200,6 +200,30 @@ def run_case(name, n, d, kind, nq, k):
 
 
 if __name__ == "__main__":
-    names = sys.argv[1:] or list(CASES)
+    names = [a for a in sys.argv[1:] if a != "whitening"] or ([] if "whitening" in sys.argv[1:] else list(CASES))
     for nm in names:
         run_case(nm, *CASES[nm])
+
+
+def run_whitening_case():
+    """PCAICAWhiteningModel.fit / transform of the reference (src/whitening/pca_ica.py) on seeded
+    clustered data: records the fitted parameters and the reference's transform of held-out rows."""
+    sys.path.insert(0, REF)
+    from src.whitening.pca_ica import PCAICAWhiteningModel
+    rng = np.random.default_rng(7)
+    centres = rng.standard_normal((12, 96)).astype(np.float32)
+    mix = rng.standard_normal((96, 96)).astype(np.float32) * 0.3 + np.eye(96, dtype=np.float32)
+    X = (centres[rng.integers(0, 12, 1500)] + 0.5 * rng.standard_normal((1500, 96)).astype(np.float32)) @ mix
+    X = X.astype(np.float32)
+    model = PCAICAWhiteningModel.fit(X[:1200], pca_dim=32)
+    held = X[1200:1264]
+    out = os.path.join(HERE, "whitening_pcaica.npz")
+    np.savez_compressed(out, mean=model.mean, pca_components=model.pca_components,
+                        pca_explained_var=model.pca_explained_var, ica_unmixing=model.ica_unmixing, eps=model.eps,
+                        x=held, y_ica=model.transform(held), y_pca=model.transform(held, is_ica=False),
+                        y_single=model.transform(held[0]))
+    print("whitening:", {k: (v.dtype, v.shape) for k, v in np.load(out).items()})
+
+
+if "whitening" in sys.argv[1:]:
+    run_whitening_case()

@@ -347,3 +347,25 @@ def test_store_sharded_predict_matches_full():
         cv = torch.cat([p[1] for p in parts], 1)
         mi, mv = parallel.merge_topk(ci, cv, k)
         assert torch.equal(mi, full_i) and torch.equal(mv, full_v)
+
+
+def test_whitening_transform_matches_reference(golden_dir, tmp_path):
+    """PCAICAWhiteningModel.transform on the device vs the reference's own outputs (fixture recorded
+    by tests/golden/make_golden.py whitening).  fp32 GEMMs: 1e-4 relative to the row scale."""
+    from rag_cobweb_b200 import PCAICAWhiteningModel
+    g = np.load(os.path.join(golden_dir, "whitening_pcaica.npz"))
+    m = PCAICAWhiteningModel(g["mean"], g["pca_components"], g["ica_unmixing"], g["pca_explained_var"], float(g["eps"]))
+    for got, want in ((m.transform(g["x"]), g["y_ica"]), (m.transform(g["x"], is_ica=False), g["y_pca"]),
+                      (m.transform(g["x"][0]), g["y_single"])):
+        assert got.shape == want.shape
+        np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-4 * np.abs(want).max())
+    # pickle layout of the reference (save / load), ragged batch sizes, and use as a wrapper front-end
+    path = str(tmp_path / "w.pkl")
+    m.save(path)
+    m2 = PCAICAWhiteningModel.load(path)
+    np.testing.assert_array_equal(m2.transform(g["x"][:3]), m.transform(g["x"])[:3])
+    big = np.tile(g["x"], (5, 1))[:301]
+    np.testing.assert_array_equal(m.transform(big)[:64], m.transform(g["x"]))
+    yd = m.transform_device(g["x"])
+    w = CobwebWrapper(corpus=[None] * len(yd), corpus_embeddings=yd)  # whitened vectors never leave the device
+    assert w.cobweb_predict_fast(yd[3], k=1, return_ids=True, is_embedding=True) == [3]
