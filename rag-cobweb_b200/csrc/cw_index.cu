@@ -50,7 +50,7 @@ __global__ void index_sumlog_kernel(cw_store s, const int *__restrict__ order, i
     }
 }
 
-// R / MB tiles: one CTA per (node tile, k tile); 256 threads, thread -> (node = tid/2, 8 attributes)
+// R / MB tiles: one CTA per (node tile, k tile); 256 threads, 256/CW_TILE_N threads per node
 __global__ void __launch_bounds__(256)
 index_tiles_kernel(cw_store s, const int *__restrict__ order, int nn, int n_ktiles, float *R, float *MB) {
     __shared__ float tr[CW_TILE_K][CW_TILE_N + 1], tm[CW_TILE_K][CW_TILE_N + 1];
@@ -58,14 +58,16 @@ index_tiles_kernel(cw_store s, const int *__restrict__ order, int nn, int n_ktil
     const int D = s.D;
     const bool cutoff = (s.flags & CW_ACUITY_CUTOFF) != 0;
     const float prior = s.prior_var;
-    const int nl = tid >> 1, half = tid & 1;
+    constexpr int TPN = 256 / CW_TILE_N;        // threads per node
+    constexpr int KPT = CW_TILE_K / TPN;        // attributes per thread
+    const int nl = tid / TPN, part = tid % TPN;
     const int b = nt * CW_TILE_N + nl;
     int node = -1;
     float cnt = 0.0f;
     if (b < nn) { node = order[b]; cnt = s.count[node]; }
 #pragma unroll
-    for (int e = 0; e < 8; e++) {
-        const int kk = half * 8 + e, d = kt * CW_TILE_K + kk;
+    for (int e = 0; e < KPT; e++) {
+        const int kk = part * KPT + e, d = kt * CW_TILE_K + kk;
         float r = 0.0f, mb = 0.0f;
         if (node >= 0 && d < D) {
             float var = cnt > 0.0f ? var_of(s.m2[(size_t)node * D + d], cnt, prior, cutoff) : prior;
