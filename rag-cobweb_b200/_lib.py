@@ -20,7 +20,7 @@ IFIT_NODE_SLACK, IFIT_POOL_SLACK = 160, 16384
 
 EXPORTS = ["cw_version", "cw_last_error", "cw_store_init", "cw_ifit", "cw_set_ifit_cluster", "cw_categorize_ctas", "cw_categorize",
            "cw_index_build", "cw_xt_floats", "cw_score_ldq", "cw_dense_node_scores", "cw_topk_chunks", "cw_dense_paths_topk",
-           "cw_predict_dense_host", "cw_whiten", "cw_ffma_peak", "cw_ffma2_peak"]
+           "cw_predict_dense_host", "cw_rank_scores_bwd", "cw_whiten", "cw_ffma_peak", "cw_ffma2_peak"]
 
 
 class CwStore(C.Structure):
@@ -73,6 +73,7 @@ def load():
     L.cw_topk_chunks.argtypes = [i64]
     L.cw_dense_paths_topk.argtypes = [C.POINTER(CwIndex), vp, i64, i64, i32, vp, vp, vp, vp, vp]
     L.cw_predict_dense_host.argtypes = [C.POINTER(CwIndex), vp, i64, i32, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp]
+    L.cw_rank_scores_bwd.argtypes = [C.POINTER(CwIndex), vp, i64, vp, vp, i64, vp, vp]
     L.cw_whiten.argtypes = [vp, i64, C.c_int32, vp, vp, C.c_int32, vp, vp, vp, vp, vp]
     L.cw_ffma_peak.argtypes = [i32, i32, i32, vp, vp]
     L.cw_ffma2_peak.argtypes = [i32, i32, i32, vp, vp]

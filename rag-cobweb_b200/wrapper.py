@@ -154,6 +154,32 @@ class DenseIndex:
         return out_sid, out_val
 
 
+class _RankScores(torch.autograd.Function):
+    """cobweb_rank_scores with a gradient w.r.t. the queries (cw_rank_scores_bwd)."""
+
+    @staticmethod
+    def forward(ctx, Q, index):
+        _, _, leaf = index.predict(Q.detach(), 0, want_leaf_scores=True)
+        ctx.index = index
+        ctx.save_for_backward(Q.detach())
+        return leaf
+
+    @staticmethod
+    def backward(ctx, grad_leaf):
+        (Q,) = ctx.saved_tensors
+        ix = ctx.index
+        nq = Q.shape[0]
+        out = torch.empty_like(Q)
+        step = max(32, min(nq, ix.chunk_queries()))
+        for lo in range(0, nq, step):
+            n = min(step, nq - lo)
+            gs = torch.empty((ix.nn, n), dtype=torch.float32, device=Q.device)
+            g = grad_leaf[lo:lo + n].contiguous().to(torch.float32)
+            _lib.check(_lib.load().cw_rank_scores_bwd(C.byref(ix.ix), Q[lo:lo + n].data_ptr(), n, g.data_ptr(), gs.data_ptr(),
+                                                      n, out[lo:lo + n].data_ptr(), _lib.stream_ptr()), "cw_rank_scores_bwd")
+        return out, None
+
+
 class CobwebWrapper:
     def __init__(self, corpus=None, corpus_embeddings=None, encode_func=lambda x: x):
         _lib.require_cuda()
@@ -316,8 +342,14 @@ class CobwebWrapper:
         return ids, vals
 
     def rank_scores_batch(self, Q):
-        """Batched cobweb_rank_scores: [nq, L] leaf scores indexed by sentence id."""
+        """Batched cobweb_rank_scores: [nq, L] leaf scores indexed by sentence id.  Differentiable
+        w.r.t. Q when Q is a CUDA tensor that requires grad (the training use of the reference,
+        src/training/cobweb_query_train.py:104-126)."""
         self.build_prediction_index()
+        if torch.is_tensor(Q) and Q.requires_grad:
+            Qd = Q.to(device=self.device, dtype=torch.float32)
+            Qd = Qd.reshape(1, -1) if Qd.dim() == 1 else Qd
+            return _RankScores.apply(Qd.contiguous(), self._index)
         _, _, leaf = self._index.predict(self.tree._as_device_mat(Q), 0, want_leaf_scores=True)
         return leaf
 
@@ -337,12 +369,14 @@ class CobwebWrapper:
         return self.cobweb_predict_indexed(input, k, return_ids, is_embedding)
 
     def cobweb_rank_scores(self, input, is_embedding=False):
-        """CobwebWrapper.cobweb_rank_scores (CobwebWrapper.py:267-294).  Forward only (autograd
-        w.r.t. the query is a SURVEY 8f 'next' row)."""
+        """CobwebWrapper.cobweb_rank_scores (CobwebWrapper.py:267-294); differentiable w.r.t. a tensor
+        input that requires grad, like the reference's torch expression."""
         self.build_prediction_index()
         if len(self.sentences) == 0:
             return torch.empty(0, device=self.device)
         x = input if is_embedding else self.encode_func([input])[0]
+        if torch.is_tensor(x) and x.requires_grad:
+            return self.rank_scores_batch(x.reshape(1, -1))[0]
         return self.rank_scores_batch(self.tree._as_device_vec(x).reshape(1, -1))[0]
 
     # ------------------------------------------------------------------ best-first predict

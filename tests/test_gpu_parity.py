@@ -369,3 +369,45 @@ def test_whitening_transform_matches_reference(golden_dir, tmp_path):
     yd = m.transform_device(g["x"])
     w = CobwebWrapper(corpus=[None] * len(yd), corpus_embeddings=yd)  # whitened vectors never leave the device
     assert w.cobweb_predict_fast(yd[3], k=1, return_ids=True, is_embedding=True) == [3]
+
+
+def test_rank_scores_gradient_matches_torch_autograd():
+    """Backward of cobweb_rank_scores w.r.t. the query against torch autograd of the reference's
+    own expression (CobwebWrapper.py:283-292) evaluated in float64 on the oracle's index arrays."""
+    n, d, nq = 500, 48, 37
+    x = synth.corpus(n, d, "whitened", seed=0)
+    x[100:110] = x[5:15]
+    w = CobwebWrapper(corpus=[None] * n, corpus_embeddings=x)
+    ref = OracleTree(d)
+    ref.ifit(x)
+    ix = ref.build_index(level_weights=[1.0, 0.5, 2.0])
+    w.set_level_weights([1.0, 0.5, 2.0])
+    q, _ = synth.queries(x, nq, "whitened", seed=1)
+    rng = np.random.default_rng(5)
+    gl = rng.standard_normal((nq, n)).astype(np.float32)
+    # engine
+    Q = torch.from_numpy(q).cuda().requires_grad_(True)
+    leaf = w.rank_scores_batch(Q)
+    (leaf * torch.from_numpy(gl).cuda()).sum().backward()
+    got = Q.grad.cpu().numpy()
+    # torch reference (float64): node log-probs, path product as a dense matrix, autograd
+    M, V = torch.from_numpy(ix["means"]).double(), torch.from_numpy(ix["vars"]).double()
+    P = torch.zeros(n, M.shape[0], dtype=torch.float64)
+    for l in range(n):
+        for j, b in enumerate(ix["path_idx"][l]):
+            if b >= 0:
+                P[l, b] += float(ix["path_w"][l, j])
+    Qr = torch.from_numpy(q).double().requires_grad_(True)
+    s_nodes = -0.5 * (torch.log(V).sum(1)[None, :] + (((Qr[:, None, :] - M[None]) ** 2) / V[None]).sum(2))
+    leaf_r = s_nodes @ P.T
+    (leaf_r * torch.from_numpy(gl).double()).sum().backward()
+    want = Qr.grad.numpy()
+    np.testing.assert_allclose(leaf.detach().cpu().numpy(), leaf_r.detach().numpy(), rtol=1e-5, atol=1e-3)
+    np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-4 * np.abs(want).max())
+    # single-query reference-style call: gradient of the sum of all leaf scores
+    x1 = torch.from_numpy(q[0]).cuda().requires_grad_(True)
+    w.cobweb_rank_scores(x1, is_embedding=True).sum().backward()
+    x1r = torch.from_numpy(q[0]).double().requires_grad_(True)
+    s1 = -0.5 * (torch.log(V).sum(1) + (((x1r[None, :] - M) ** 2) / V).sum(1))
+    (s1 @ P.T).sum().backward()
+    np.testing.assert_allclose(x1.grad.cpu().numpy(), x1r.grad.numpy(), rtol=1e-4, atol=1e-4 * np.abs(x1r.grad.numpy()).max())
