@@ -458,14 +458,11 @@ extern "C" int cw_dense_node_scores(const cw_index *ix, const float *Q, int64_t 
     cudaStream_t st = (cudaStream_t)stream;
     const int n_qtiles = (int)((nq + TQ - 1) / TQ);
     int rc = 0;
-    static bool configured = false;
-    if (!configured) {
-        rc = cw_check_cuda(cudaFuncSetAttribute(dense_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                score_smem_bytes()),
-                           "cw_dense: smem attribute");
-        if (rc) return rc;
-        configured = true;
-    }
+    // per call: the attribute is per device, and a process may drive several
+    rc = cw_check_cuda(cudaFuncSetAttribute(dense_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            score_smem_bytes()),
+                       "cw_dense: smem attribute");
+    if (rc) return rc;
     tile_queries_kernel<<<dim3(n_qtiles, ix->n_ktiles), 256, 0, st>>>(Q, nq, ix->D, ix->n_ktiles, xt_scratch);
     dense_score_kernel<<<dim3(n_qtiles, ix->n_ntiles), SCORE_THREADS, score_smem_bytes(), st>>>(
         xt_scratch, ix->R, ix->MB, ix->sumlog, node_scores, ldq, ix->n_ktiles);
@@ -511,13 +508,11 @@ extern "C" int cw_dense_paths_topk(const cw_index *ix, const float *node_scores,
     float *cand_s = reinterpret_cast<float *>(scratch);
     int *cand_i = scratch + (size_t)nq * n_chunks * (k > 0 ? k : 1);
     const size_t smem = (size_t)ix->max_len * sizeof(double) + (size_t)wpb * per_warp;
-    static size_t configured = 48 * 1024;
-    if (smem > configured) {
+    if (smem > 48 * 1024) {
         int rc = cw_check_cuda(cudaFuncSetAttribute(paths_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                     (int)smem),
                                "cw_dense_paths_topk: smem attribute");
         if (rc) return rc;
-        configured = smem;
     }
     paths_topk_kernel<<<dim3(n_chunks, (unsigned)gblocks), wpb * 32, smem, st>>>(
         node_scores, (unsigned)ldq, nq, ix->n_pos, ix->max_len, ix->path_idx, reinterpret_cast<const int4 *>(ix->pos_rec),

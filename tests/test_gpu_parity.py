@@ -101,6 +101,22 @@ def test_ifit_cluster_sizes_agree():
         L.cw_set_ifit_cluster(0)
 
 
+def test_child_pool_compaction_keeps_the_tree():
+    """Child lists are rewritten contiguously (leaked chunks dropped) without changing the tree, and
+    inserts continue bit-exactly afterwards."""
+    x, tree, ref = build_pair(2400, 64, "whitened")
+    tree.ifit_batch(x[:1200], tag_sentences=True)
+    used_before = int(tree.store.header()[3])
+    b0 = tree.bfs()
+    tree.store.compact_pool()
+    assert int(tree.store.header()[3]) <= used_before
+    b1 = tree.bfs()
+    assert all(np.array_equal(b0[k], b1[k]) for k in ("order", "parent", "count", "nchild", "nsent"))
+    leaves2 = tree.ifit_batch(x[1200:], tag_sentences=True)
+    rl = ref.ifit(x)
+    assert_same_tree(tree, ref, leaves2.cpu().numpy(), rl[1200:])
+
+
 def test_ifit_capacity_growth_midway():
     x, tree, ref = build_pair(3000, 64, "unit")
     tree.IFIT_CHUNK = 700  # several launches, several reallocations of the store
