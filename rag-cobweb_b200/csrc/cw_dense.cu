@@ -261,6 +261,7 @@ paths_topk_kernel(const float *__restrict__ ST, unsigned ldq, long long nq, int 
     float *Ls = wt + wt_n + (size_t)warp * k * 32;                                                // [32 lanes][k]
     int *Li = reinterpret_cast<int *>(wt + wt_n + (size_t)wpb * k * 32) + (size_t)warp * k * 32;  // [32 lanes][k]
     float *St = wt + wt_n + (size_t)2 * wpb * k * 32 + (size_t)warp * max_len * 32;               // [max_len][32]
+    float *wl = wt + wt_n + (size_t)2 * wpb * k * 32 + (size_t)wpb * max_len * 32 + (size_t)warp * max_len;  // [max_len]
     for (int i = threadIdx.x; i < max_len; i += blockDim.x) lw[i] = level_w[i];
     const float NEG_INF = -__int_as_float(0x7f800000);
     for (int i = lane; i < 32 * k; i += 32) { Ls[i] = NEG_INF; Li[i] = -1; }
@@ -274,6 +275,7 @@ paths_topk_kernel(const float *__restrict__ ST, unsigned ldq, long long nq, int 
     const int p0 = chunk * chunk_len, p1 = min(n_pos, p0 + chunk_len);
     float thr_s = NEG_INF;
     int thr_i = -1;
+    int wl_len = -1;  // path length the per-warp weight row wl[] was computed for
     // one position ahead: its record and its leaf-level score are in flight while the current
     // position is processed (the leaf row is the one read that is new for almost every position)
     const int4 *rec = pos_rec + p0;
@@ -289,15 +291,20 @@ paths_topk_kernel(const float *__restrict__ ST, unsigned ldq, long long nq, int 
         }
         const int len = rc.x;
         const int m = p == p0 ? 0 : rc.y;
-        const double dlen = (double)len;
+        if (len != wl_len) {  // rare: positions are sorted by depth, so len changes a handful of times per chunk
+            __syncwarp();
+            for (int j = lane; j < len; j += 32) wl[j] = (float)(lw[j] / (double)len);
+            wl_len = len;
+            __syncwarp();
+        }
         float acc = m > 0 ? St[(m - 1) * 32 + lane] : 0.0f;
         for (int j = m; j < len - 1; j++) {  // rare: the parent (or higher) changed as well
             const int b = path_pm[(size_t)p * max_len + j];
-            acc = __fmaf_rn((float)(lw[j] / dlen), col[(size_t)(unsigned)b * ldq], acc);
+            acc = __fmaf_rn(wl[j], col[(size_t)(unsigned)b * ldq], acc);
             St[j * 32 + lane] = acc;
         }
         if (m < len) {
-            acc = __fmaf_rn((float)(lw[len - 1] / dlen), leaf_c, acc);
+            acc = __fmaf_rn(wl[len - 1], leaf_c, acc);
             St[(len - 1) * 32 + lane] = acc;
         }
         const int sid = rc.w;
@@ -487,7 +494,7 @@ extern "C" int cw_dense_paths_topk(const cw_index *ix, const float *node_scores,
     cudaStream_t st = (cudaStream_t)stream;
     // warps per CTA: per warp the per-lane top-k lists take k*256 bytes of shared memory and the
     // partial-sum stack max_len*128 bytes
-    const size_t per_warp = (size_t)k * 256 + (size_t)ix->max_len * 128;
+    const size_t per_warp = (size_t)k * 256 + (size_t)ix->max_len * 132;
     int wpb = (int)(98304 / per_warp);
     if (wpb > 8) wpb = 8;
     if (wpb < 1) wpb = 1;
