@@ -237,6 +237,12 @@ __device__ __forceinline__ bool cand_better(float as, int ai, float bs, int bi) 
     return ai < bi;
 }
 
+// Rare path of the kernel below (the path length changes a handful of times per chunk); kept out
+// of line so that its binary64 division does not inflate the hot loop's register allocation.
+__device__ __noinline__ void fill_weight_row(float *wl, const double *lw, int len, int lane) {
+    for (int j = lane; j < len; j += 32) wl[j] = (float)(lw[j] / (double)len);
+}
+
 // grid (position chunks, groups of `wpb` query groups): warp = 32 queries (lane = query) x one
 // chunk of sentence positions.  Positions are in tree order, so consecutive paths share a
 // prefix (siblings differ only in the leaf); the index stores per position
@@ -246,7 +252,7 @@ __device__ __forceinline__ bool cand_better(float as, int ai, float bs, int bi) 
 // as a full root-to-leaf chain (bit-equal to torch.sparse.mm on the reference's side).  Each
 // level is one coalesced 128-byte read of the node-major score matrix.  Every lane keeps its
 // query's sorted top-k in shared memory ([rank][lane]) behind a register threshold.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 5)
 paths_topk_kernel(const float *__restrict__ ST, unsigned ldq, long long nq, int n_pos, int max_len,
                   const int *__restrict__ path_pm, const int4 *__restrict__ pos_rec,
                   const double *__restrict__ level_w, int k, float *leaf_scores, float *cand_s, int *cand_i,
@@ -293,7 +299,7 @@ paths_topk_kernel(const float *__restrict__ ST, unsigned ldq, long long nq, int 
         const int m = p == p0 ? 0 : rc.y;
         if (len != wl_len) {  // rare: positions are sorted by depth, so len changes a handful of times per chunk
             __syncwarp();
-            for (int j = lane; j < len; j += 32) wl[j] = (float)(lw[j] / (double)len);
+            fill_weight_row(wl, lw, len, lane);
             wl_len = len;
             __syncwarp();
         }
@@ -312,6 +318,30 @@ paths_topk_kernel(const float *__restrict__ ST, unsigned ldq, long long nq, int 
         // top-k: lanes whose candidate beats their query's k-th best are served one at a time by
         // the whole warp (lane r handles rank r of that query's list): no divergent shifting loops
         unsigned need = __ballot_sync(0xffffffffu, k > 0 && qvalid && cand_better(acc, sid, thr_s, thr_i));
+        if (k <= 32) {
+            // one rank per lane: read, ballot the insertion point, shift by one, done
+            while (need) {
+                const int L = __ffs(need) - 1;
+                need &= need - 1;
+                const float cv = __shfl_sync(0xffffffffu, acc, L);
+                const int base = L * k;
+                float es = NEG_INF;
+                int ei = -1;
+                if (lane < k) { es = Ls[base + lane]; ei = Li[base + lane]; }
+                // empty ranks hold -inf, so they never beat a finite candidate
+                const int pos = __popc(__ballot_sync(0xffffffffu, es > cv || (es == cv && ei < sid)));
+                const float ps = __shfl_sync(0xffffffffu, es, (k - 2) & 31);
+                const int pi = __shfl_sync(0xffffffffu, ei, (k - 2) & 31);
+                if (lane >= pos && lane + 1 < k) { Ls[base + lane + 1] = es; Li[base + lane + 1] = ei; }
+                if (lane == pos) { Ls[base + lane] = cv; Li[base + lane] = sid; }
+                if (lane == L) {  // new k-th best: old rank k-2, unless the candidate itself landed on rank k-1
+                    const bool cand_last = (k < 2) || (pos == k - 1);
+                    thr_s = cand_last ? cv : ps;
+                    thr_i = cand_last ? sid : pi;
+                }
+                __syncwarp();
+            }
+        }
         while (need) {
             const int L = __ffs(need) - 1;
             need &= need - 1;

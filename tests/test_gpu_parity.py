@@ -427,3 +427,35 @@ def test_rank_scores_gradient_matches_torch_autograd():
     s1 = -0.5 * (torch.log(V).sum(1) + (((x1r[None, :] - M) ** 2) / V).sum(1))
     (s1 @ P.T).sum().backward()
     np.testing.assert_allclose(x1.grad.cpu().numpy(), x1r.grad.numpy(), rtol=1e-4, atol=1e-4 * np.abs(x1r.grad.numpy()).max())
+
+
+def test_wrapper_input_conventions():
+    """The reference's callers pass lists, numpy rows, tensors and text + encode_func
+    (CobwebWrapper.py:13-80, benchmark_utils.py:465-581): all of them work."""
+    rng = np.random.default_rng(11)
+    vocab = {f"doc {i}": rng.standard_normal(24).astype(np.float32) for i in range(60)}
+    encode = lambda texts: np.stack([vocab[t] for t in texts])  # noqa: E731
+    texts = list(vocab)
+    w_text = CobwebWrapper(corpus=texts, encode_func=encode)                      # text only
+    emb = encode(texts)
+    w_np = CobwebWrapper(corpus=texts, corpus_embeddings=emb)                     # numpy matrix
+    w_list = CobwebWrapper(corpus=texts, corpus_embeddings=emb.tolist())          # python lists
+    w_t = CobwebWrapper(corpus=None, corpus_embeddings=torch.from_numpy(emb))     # tensor, embedding-only entries
+    for w in (w_np, w_list, w_t):
+        assert np.array_equal(w.tree.bfs()["parent"], w_text.tree.bfs()["parent"])
+    assert w_t.sentences == [None] * 60 and len(w_text) == 60
+    # query by text (encode_func), by numpy row positionally like retrieve_cobweb_basic, by tensor
+    assert w_text.cobweb_predict_fast("doc 7", k=1) == ["doc 7"]
+    assert w_np.cobweb_predict_fast(emb[7], k=1, return_ids=True) == [7]          # identity encode_func([q])[0]
+    assert w_np.cobweb_predict(torch.from_numpy(emb[9]), k=1, return_ids=True, is_embedding=True) == [9]
+    # add_sentences appends with running ids and invalidates the index
+    w_np.build_prediction_index()
+    extra = rng.standard_normal((3, 24)).astype(np.float32)
+    w_np.add_sentences(["x", "y", "z"], extra)
+    assert not w_np._prediction_index_valid and len(w_np) == 63
+    assert w_np.cobweb_predict_fast(extra[1], k=1, is_embedding=True) == ["y"]
+    assert set(w_np.sentence_to_node) == set(range(63))
+    leaf = w_np.sentence_to_node[61]
+    assert 61 in w_np.cobweb_predict(extra[1], k=1, return_ids=True, is_embedding=True) and leaf.children == []
+    info = w_np.get_weight_schedule_info()
+    assert info["schedule_type"] is None and w_np.get_prediction_index_info()["index_valid"]
