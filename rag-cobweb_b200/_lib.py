@@ -16,11 +16,13 @@ CW_USE_INFO, CW_USE_KL, CW_ACUITY_CUTOFF = 1, 2, 4
 HDR_WORDS = 16
 SCRATCH_WORDS = 16384
 TILE_N, TILE_K, MAX_K, MAX_D, MAX_CHILDREN = 128, 16, 128, 4096, 2048
+TC_TILE_Q, TC_TILE_N, TC_SLAB_D = 128, 256, 16
 IFIT_NODE_SLACK, IFIT_POOL_SLACK = 160, 16384
 
 EXPORTS = ["cw_version", "cw_last_error", "cw_store_init", "cw_ifit", "cw_set_ifit_cluster", "cw_categorize_ctas", "cw_categorize",
            "cw_index_build", "cw_xt_floats", "cw_score_ldq", "cw_dense_node_scores", "cw_topk_chunks", "cw_dense_paths_topk",
-           "cw_predict_dense_host", "cw_rank_scores_bwd", "cw_whiten", "cw_ffma_peak", "cw_ffma2_peak"]
+           "cw_predict_dense_host", "cw_tc_b_bytes", "cw_tc_a_bytes", "cw_tc_index_build",
+           "cw_dense_node_scores_tc", "cw_rank_scores_bwd", "cw_whiten", "cw_ffma_peak", "cw_ffma2_peak"]
 
 
 class CwStore(C.Structure):
@@ -36,6 +38,11 @@ class CwIndex(C.Structure):
                 ("R", C.c_void_p), ("MB", C.c_void_p), ("sumlog", C.c_void_p),
                 ("n_pos", C.c_int32), ("max_len", C.c_int32),
                 ("path_idx", C.c_void_p), ("level_w", C.c_void_p), ("pos_rec", C.c_void_p)]
+
+
+class CwTcIndex(C.Structure):
+    _fields_ = [("D", C.c_int32), ("nn", C.c_int32), ("n_ntiles", C.c_int32), ("n_slabs", C.c_int32),
+                ("B", C.c_void_p), ("hconst", C.c_void_p)]
 
 
 class CobwebB200Error(RuntimeError):
@@ -72,7 +79,14 @@ def load():
     L.cw_topk_chunks.restype = i64
     L.cw_topk_chunks.argtypes = [i64]
     L.cw_dense_paths_topk.argtypes = [C.POINTER(CwIndex), vp, i64, i64, i32, vp, vp, vp, vp, vp]
-    L.cw_predict_dense_host.argtypes = [C.POINTER(CwIndex), vp, i64, i32, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp]
+    L.cw_predict_dense_host.argtypes = [C.POINTER(CwIndex), C.POINTER(CwTcIndex), vp, i64, i32, vp, vp, vp, i64, vp, vp, vp, vp,
+                                        vp, vp]
+    L.cw_tc_b_bytes.restype = i64
+    L.cw_tc_b_bytes.argtypes = [C.c_int32, C.c_int32]
+    L.cw_tc_a_bytes.restype = i64
+    L.cw_tc_a_bytes.argtypes = [i64, C.c_int32]
+    L.cw_tc_index_build.argtypes = [C.POINTER(CwStore), vp, C.c_int32, vp, C.POINTER(CwTcIndex), vp]
+    L.cw_dense_node_scores_tc.argtypes = [C.POINTER(CwTcIndex), vp, i64, vp, vp, i64, vp]
     L.cw_rank_scores_bwd.argtypes = [C.POINTER(CwIndex), vp, i64, vp, vp, i64, vp, vp]
     L.cw_whiten.argtypes = [vp, i64, C.c_int32, vp, vp, C.c_int32, vp, vp, vp, vp, vp]
     L.cw_ffma_peak.argtypes = [i32, i32, i32, vp, vp]

@@ -559,8 +559,8 @@ extern "C" int cw_dense_paths_topk(const cw_index *ix, const float *node_scores,
     return cw_check_cuda(cudaGetLastError(), "cw_dense_paths_topk");
 }
 
-extern "C" int cw_predict_dense_host(const cw_index *ix, const float *Q_host, int64_t nq, int k, float *Q_dev,
-                                     float *xt_scratch, float *node_scores, int64_t ldq, int32_t *out_sid_dev, float *out_score_dev,
+extern "C" int cw_predict_dense_host(const cw_index *ix, const cw_tc_index *tx, const float *Q_host, int64_t nq, int k,
+                                     float *Q_dev, float *xt_scratch, float *node_scores, int64_t ldq, int32_t *out_sid_dev, float *out_score_dev,
                                      int32_t *scratch, int32_t *out_sid_host, float *out_score_host, void *stream) {
     if (!ix || !Q_host || !Q_dev || !out_sid_host || !out_score_host || k < 1) {
         cw_set_error("cw_predict_dense_host: bad argument");
@@ -570,7 +570,9 @@ extern "C" int cw_predict_dense_host(const cw_index *ix, const float *Q_host, in
     int rc = cw_check_cuda(cudaMemcpyAsync(Q_dev, Q_host, (size_t)nq * ix->D * sizeof(float), cudaMemcpyHostToDevice, st),
                            "cw_predict_dense_host: H2D");
     if (rc) return rc;
-    if ((rc = cw_dense_node_scores(ix, Q_dev, nq, xt_scratch, node_scores, ldq, stream))) return rc;
+    rc = tx ? cw_dense_node_scores_tc(tx, Q_dev, nq, xt_scratch, node_scores, ldq, stream)
+            : cw_dense_node_scores(ix, Q_dev, nq, xt_scratch, node_scores, ldq, stream);
+    if (rc) return rc;
     if ((rc = cw_dense_paths_topk(ix, node_scores, ldq, nq, k, nullptr, out_sid_dev, out_score_dev, scratch, stream)))
         return rc;
     rc = cw_check_cuda(cudaMemcpyAsync(out_sid_host, out_sid_dev, (size_t)nq * k * sizeof(int32_t),

@@ -1,0 +1,410 @@
+// cw_tensor.cu -- the dense node score of cobweb_predict_indexed / cobweb_rank_scores
+// (src/cobweb/CobwebWrapper.py:232-236, 283-287) as a tensor-core contraction on tcgen05.
+//
+//   s[q,n] = -0.5*(sumlog[n] + sum_d (x_qd - mu_nd)^2 / var_nd)
+//          = h[n] - 0.5 * sum_f A[q,f] * B[n,f]
+//   A[q, .] = (x_d^2 , x_d)            B[n, .] = (1/var_nd , -2 mu_nd/var_nd)
+//   h[n]    = -0.5*(sumlog[n] + sum_d mu_nd^2/var_nd)          (binary64 at index build)
+//
+// A single TF32 product keeps 11 significant bits, far too few where a query sits next to a
+// leaf (terms of size ~|x|^2/var cancel down to the squared distance).  Every operand is
+// therefore split into two TF32 numbers, v = hi + lo (22-23 significant bits), and the product
+// is evaluated as hi*hi + hi*lo + lo*hi -- three tcgen05.mma (kind::tf32, fp32 accumulate in
+// TMEM) per K step; the dropped lo*lo term is below 2^-22 relative.  Measured against the
+// FP32-pipe kernel (cw_dense.cu) the node scores agree to ~1e-6 relative (tests/test_gpu_parity.py).
+//
+// Kernel shape: persistent, one CTA per SM, 192 threads:
+//   warp 0   producer: cp.async.bulk (TMA bulk copy) of one 96 KB stage = {A_hi, A_lo} 128 queries x 32
+//            features + {B_hi, B_lo} 256 nodes x 32 features; the operands are stored in HBM as
+//            the exact shared-memory image (K-major rows of 128 bytes, 128-byte swizzle), so a
+//            stage is two contiguous copies and needs no tensor map;
+//   warp 1   MMA issuer: one lane issues 12 tcgen05.mma (M=128, N=256, K=8) per stage and
+//            tcgen05.commit's the stage back to the producer / the accumulator to the epilogue;
+//   warps 2-5 epilogue: tcgen05.ld of the 128x256 fp32 accumulator (lane = query, column =
+//            node), h[n] - 0.5*acc, written NODE-major (one 128-byte line per warp store);
+// two accumulators (2 x 256 TMEM columns) so the epilogue of tile t overlaps the MMAs of t+1.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/cobweb_b200.h"
+
+void cw_set_error(const char *fmt, ...);
+int cw_check_cuda(cudaError_t e, const char *what);
+
+namespace cwt {
+
+constexpr int TM = CW_TC_TILE_Q;     // queries per tile  (UMMA M)
+constexpr int TN = CW_TC_TILE_N;     // nodes per tile    (UMMA N)
+constexpr int SD = CW_TC_SLAB_D;     // attributes per K slab
+constexpr int ROWB = 128;            // bytes per operand row in a slab (32 tf32)
+constexpr int A_IMG = TM * ROWB;     // 16 KB
+constexpr int B_IMG = TN * ROWB;     // 32 KB
+constexpr int A_BYTES = 2 * A_IMG;   // hi + lo
+constexpr int B_BYTES = 2 * B_IMG;
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;  // 96 KB
+constexpr int NSTAGE = 2;
+constexpr int NACC = 2;
+constexpr int THREADS = 192;
+constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+static_assert(SD * 2 * 4 == ROWB, "a slab row is 16 x^2 features + 16 x features");
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol error traps (the launch fails with an error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 28)) __trap();
+    }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+// ---- tcgen05 wrappers
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, one 128 x 256 x 8 TF32 MMA
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp): K-major operand,
+// rows of 128 bytes, 128-byte swizzle; 8-row groups 1024 bytes apart.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);  // start address, 16-byte units
+    d |= (uint64_t)1 << 16;                    // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                    // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+    return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, M x N
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+#define CW_TMEM_LD32(taddr, v)                                                                                     \
+    asm volatile(                                                                                                  \
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                  \
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                                  \
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"                  \
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),          \
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),    \
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),  \
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])   \
+        : "r"(taddr)                                                                                               \
+        : "memory")
+
+// v = hi + lo with hi, lo representable in TF32 (round to nearest; v - hi is exact in binary32)
+__device__ __forceinline__ void split_tf32(float v, float &hi, float &lo) {
+    uint32_t h, l;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
+    hi = __uint_as_float(h);
+    const float rem = v - hi;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(rem));
+    lo = __uint_as_float(l);
+}
+
+// byte offset of 16-byte chunk c (0..7) of row r inside a 128-byte-swizzled operand image
+__device__ __forceinline__ int swz_off(int r, int c) { return r * ROWB + ((c ^ (r & 7)) << 4); }
+
+// ------------------------------------------------------------------ the scoring kernel
+__global__ void __launch_bounds__(THREADS, 1)
+tc_score_kernel(const unsigned char *__restrict__ A, const unsigned char *__restrict__ B,
+                const float *__restrict__ hconst, float *__restrict__ out, long long ldq, int n_qtiles, int n_ntiles,
+                int n_slabs) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // swizzle atoms need 1024-byte alignment
+    const uint32_t bars = base + NSTAGE * STAGE_BYTES;
+    // barrier words: full[NSTAGE], empty[NSTAGE], acc_full[NACC], acc_empty[NACC], then the TMEM base address
+    const uint32_t full0 = bars, empty0 = bars + 8 * NSTAGE, accf0 = bars + 16 * NSTAGE, acce0 = accf0 + 8 * NACC;
+    const uint32_t tmem_slot = acce0 + 8 * NACC;
+    uint32_t *tmem_slot_ptr = reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSTAGE; s++) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, 1);
+        }
+        for (int a = 0; a < NACC; a++) {
+            mbar_init(accf0 + 8 * a, 1);
+            mbar_init(acce0 + 8 * a, 4);  // one arrival per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {  // TMEM: all 512 columns (two 128 x 256 fp32 accumulators); this warp also frees them
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    const long long n_tiles = (long long)n_qtiles * n_ntiles;
+
+    if (warp == 0) {
+        // ===== producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                const int nt = (int)(t / n_qtiles), qt = (int)(t % n_qtiles);
+                const unsigned char *asrc = A + (size_t)qt * n_slabs * A_BYTES;
+                const unsigned char *bsrc = B + (size_t)nt * n_slabs * B_BYTES;
+                for (int s = 0; s < n_slabs; s++) {
+                    mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                    const uint32_t sb = base + stage * STAGE_BYTES;
+                    mbar_arrive_expect_tx(full0 + 8 * stage, STAGE_BYTES);
+                    bulk_g2s(sb, asrc + (size_t)s * A_BYTES, A_BYTES, full0 + 8 * stage);
+                    bulk_g2s(sb + A_BYTES, bsrc + (size_t)s * B_BYTES, B_BYTES, full0 + 8 * stage);
+                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===== MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(TM, TN);
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, aphase = 0;
+            for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                mbar_wait(acce0 + 8 * acc, aphase ^ 1);  // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d = tmem_base + (uint32_t)(acc * TN);
+                for (int s = 0; s < n_slabs; s++) {
+                    mbar_wait(full0 + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint32_t sb = base + stage * STAGE_BYTES;
+                    const uint64_t a_hi = make_smem_desc(sb), a_lo = make_smem_desc(sb + A_IMG);
+                    const uint64_t b_hi = make_smem_desc(sb + A_BYTES), b_lo = make_smem_desc(sb + A_BYTES + B_IMG);
+#pragma unroll
+                    for (int k = 0; k < ROWB / 32; k++) {  // 8 TF32 = 32 bytes per MMA; +2 in 16-byte address units
+                        const uint64_t ko = (uint64_t)(2 * k);
+                        tc_mma_tf32(d, a_hi + ko, b_hi + ko, idesc, (s | k) != 0);
+                        tc_mma_tf32(d, a_hi + ko, b_lo + ko, idesc, 1);
+                        tc_mma_tf32(d, a_lo + ko, b_hi + ko, idesc, 1);
+                    }
+                    tc_commit(empty0 + 8 * stage);  // stage free once these MMAs have read it
+                    if (s == n_slabs - 1) tc_commit(accf0 + 8 * acc);
+                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                }
+                if (++acc == NACC) { acc = 0; aphase ^= 1; }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===== epilogue: warp w reads TMEM lanes 32*(w%4) .. +31 (lane = query of the tile)
+        const int quarter = warp & 3;
+        int acc = 0;
+        uint32_t aphase = 0;
+        for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const int nt = (int)(t / n_qtiles), qt = (int)(t % n_qtiles);
+            mbar_wait(accf0 + 8 * acc, aphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * TN);
+            float *col = out + (long long)qt * TM + quarter * 32 + lane;
+            const long long n0 = (long long)nt * TN;
+#pragma unroll 1
+            for (int c = 0; c < TN / 32; c++) {
+                uint32_t v[32];
+                CW_TMEM_LD32(taddr + (uint32_t)(c * 32), v);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    const long long n = n0 + c * 32 + j;
+                    col[n * ldq] = fmaf(-0.5f, __uint_as_float(v[j]), __ldg(hconst + n));
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acce0 + 8 * acc);
+            if (++acc == NACC) { acc = 0; aphase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------ operand builders
+// Queries: Q [nq, D] -> A [q tile][slab][hi, lo][128 rows x 128 B swizzled]; row = (x^2 x16 | x x16)
+__global__ void __launch_bounds__(256)
+tc_queries_kernel(const float *__restrict__ Q, long long nq, int D, int n_slabs, unsigned char *A) {
+    const int qt = blockIdx.x, s = blockIdx.y, tid = threadIdx.x;
+    const int r = tid >> 1, half = tid & 1;  // half 0: squares, half 1: the values
+    const long long q = (long long)qt * TM + r;
+    unsigned char *img = A + ((size_t)qt * n_slabs + s) * A_BYTES;
+#pragma unroll
+    for (int c4 = 0; c4 < 4; c4++) {
+        float hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const int d = s * SD + c4 * 4 + e;
+            float x = (q < nq && d < D) ? Q[q * D + d] : 0.0f;
+            if (half == 0) x = x * x;
+            split_tf32(x, hi[e], lo[e]);
+        }
+        const int off = swz_off(r, half * 4 + c4);
+        *reinterpret_cast<float4 *>(img + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4 *>(img + A_IMG + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
+// Nodes: B [node tile][slab][hi, lo][256 rows x 128 B swizzled]; row = (1/var x16 | -2 mean/var x16)
+__global__ void __launch_bounds__(256)
+tc_nodes_kernel(cw_store s, const int *__restrict__ order, int nn, int n_slabs, unsigned char *B) {
+    const int nt = blockIdx.x, sl = blockIdx.y, r = threadIdx.x;
+    const int D = s.D;
+    const bool cutoff = (s.flags & CW_ACUITY_CUTOFF) != 0;
+    const float prior = s.prior_var;
+    const int b = nt * TN + r;
+    int node = -1;
+    float cnt = 0.0f;
+    if (b < nn) { node = order[b]; cnt = s.count[node]; }
+    unsigned char *img = B + ((size_t)nt * n_slabs + sl) * B_BYTES;
+#pragma unroll
+    for (int c4 = 0; c4 < 4; c4++) {
+        float ihi[4], ilo[4], mhi[4], mlo[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const int d = sl * SD + c4 * 4 + e;
+            float iv = 0.0f, mv = 0.0f;
+            if (node >= 0 && d < D) {
+                float var = prior;
+                if (cnt > 0.0f) {
+                    const float v = s.m2[(size_t)node * D + d] / cnt;  // CobwebTorchTree.compute_var
+                    var = cutoff ? (v < prior ? prior : v) : v + prior;
+                }
+                const double inv = 1.0 / (double)var;
+                iv = (float)inv;
+                mv = (float)(-2.0 * (double)s.mean[(size_t)node * D + d] * inv);
+            }
+            split_tf32(iv, ihi[e], ilo[e]);
+            split_tf32(mv, mhi[e], mlo[e]);
+        }
+        const int o1 = swz_off(r, c4), o2 = swz_off(r, 4 + c4);
+        *reinterpret_cast<float4 *>(img + o1) = make_float4(ihi[0], ihi[1], ihi[2], ihi[3]);
+        *reinterpret_cast<float4 *>(img + B_IMG + o1) = make_float4(ilo[0], ilo[1], ilo[2], ilo[3]);
+        *reinterpret_cast<float4 *>(img + o2) = make_float4(mhi[0], mhi[1], mhi[2], mhi[3]);
+        *reinterpret_cast<float4 *>(img + B_IMG + o2) = make_float4(mlo[0], mlo[1], mlo[2], mlo[3]);
+    }
+}
+
+// h[b] = -0.5*(sumlog[b] + sum_d mean^2/var) in binary64, one warp per index row; padding rows get 0.
+__global__ void __launch_bounds__(256)
+tc_hconst_kernel(cw_store s, const int *__restrict__ order, int nn, int n_rows, const float *__restrict__ sumlog,
+                 float *hconst) {
+    const int b = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= n_rows) return;
+    if (b >= nn) {
+        if (lane == 0) hconst[b] = 0.0f;
+        return;
+    }
+    const int D = s.D, node = order[b];
+    const bool cutoff = (s.flags & CW_ACUITY_CUTOFF) != 0;
+    const float prior = s.prior_var, cnt = s.count[node];
+    double acc = 0.0;
+    for (int d = lane; d < D; d += 32) {
+        float var = prior;
+        if (cnt > 0.0f) {
+            const float v = s.m2[(size_t)node * D + d] / cnt;
+            var = cutoff ? (v < prior ? prior : v) : v + prior;
+        }
+        const double mu = (double)s.mean[(size_t)node * D + d];
+        acc += mu * mu / (double)var;
+    }
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) hconst[b] = (float)(-0.5 * ((double)sumlog[b] + acc));
+}
+
+}  // namespace cwt
+
+using namespace cwt;
+
+extern "C" int64_t cw_tc_a_bytes(int64_t nq, int32_t D) {
+    return ((nq + TM - 1) / TM) * (int64_t)((D + SD - 1) / SD) * A_BYTES;
+}
+extern "C" int64_t cw_tc_b_bytes(int32_t nn, int32_t D) {
+    return (int64_t)((nn + TN - 1) / TN) * (int64_t)((D + SD - 1) / SD) * B_BYTES;
+}
+
+extern "C" int cw_tc_index_build(const cw_store *s, const int32_t *order, int32_t nn, const float *sumlog,
+                                 const cw_tc_index *tx, void *stream) {
+    if (!s || !order || !sumlog || !tx || nn < 1 || tx->D != s->D || tx->nn != nn || !tx->B || !tx->hconst ||
+        tx->n_ntiles != (nn + TN - 1) / TN || tx->n_slabs != (s->D + SD - 1) / SD) {
+        cw_set_error("cw_tc_index_build: bad argument / inconsistent header");
+        return CW_E_ARG;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    tc_nodes_kernel<<<dim3(tx->n_ntiles, tx->n_slabs), 256, 0, st>>>(*s, order, nn, tx->n_slabs,
+                                                                    reinterpret_cast<unsigned char *>(tx->B));
+    const int n_rows = tx->n_ntiles * TN;
+    tc_hconst_kernel<<<(n_rows + 7) / 8, 256, 0, st>>>(*s, order, nn, n_rows, sumlog, tx->hconst);
+    return cw_check_cuda(cudaGetLastError(), "cw_tc_index_build");
+}
+
+extern "C" int cw_dense_node_scores_tc(const cw_tc_index *tx, const float *Q, int64_t nq, void *a_scratch,
+                                       float *node_scores, int64_t ldq, void *stream) {
+    if (!tx || !Q || !a_scratch || !node_scores || nq < 0 || ldq < cw_score_ldq(nq) || (ldq % TM)) {
+        cw_set_error("cw_dense_node_scores_tc: bad argument (ldq must be >= cw_score_ldq(nq) and a multiple of %d)", TM);
+        return CW_E_ARG;
+    }
+    if (nq == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n_qtiles = (int)((nq + TM - 1) / TM);
+    int rc = cw_check_cuda(cudaFuncSetAttribute(tc_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES),
+                           "cw_dense_node_scores_tc: smem attribute");
+    if (rc) return rc;
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    tc_queries_kernel<<<dim3(n_qtiles, tx->n_slabs), 256, 0, st>>>(Q, nq, tx->D, tx->n_slabs,
+                                                                  reinterpret_cast<unsigned char *>(a_scratch));
+    const long long n_tiles = (long long)n_qtiles * tx->n_ntiles;
+    const int grid = (int)(n_tiles < sms ? n_tiles : sms);
+    tc_score_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(reinterpret_cast<const unsigned char *>(a_scratch),
+                                                       reinterpret_cast<const unsigned char *>(tx->B), tx->hconst,
+                                                       node_scores, ldq, n_qtiles, tx->n_ntiles, tx->n_slabs);
+    return cw_check_cuda(cudaGetLastError(), "cw_dense_node_scores_tc");
+}

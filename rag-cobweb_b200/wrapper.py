@@ -27,6 +27,9 @@ class DenseIndex:
     """Device-resident prediction index (build_prediction_index, CobwebWrapper.py:91-208)."""
 
     SCORE_BUDGET_BYTES = 8 << 30  # node-score scratch per query chunk
+    # where the node scores are computed: "fp32" = FP32 pipe, (x*r + mb)^2 per triple (cw_dense.cu);
+    # "tf32x3" = tcgen05 contraction with hi/lo-split TF32 operands (cw_tensor.cu), ~1e-6 relative to "fp32"
+    MODES = ("fp32", "tf32x3")
 
     def __init__(self, tree, leaf_of_sentence, level_weights=None, sentence_ids=None):
         """leaf_of_sentence[i] = leaf node id of sentence i.  sentence_ids (optional, sorted global
@@ -49,7 +52,9 @@ class DenseIndex:
         d = tree.d
         self.n_ntiles = (self.nn + _lib.TILE_N - 1) // _lib.TILE_N
         self.n_ktiles = (d + _lib.TILE_K - 1) // _lib.TILE_K
-        self.ld = self.n_ntiles * _lib.TILE_N  # rows of the node-major score matrix
+        # rows of the node-major score matrix (covers the 128-row tiles of the FP32 kernel and the 256-row
+        # tiles of the tensor-core kernel)
+        self.ld = (self.nn + _lib.TC_TILE_N - 1) // _lib.TC_TILE_N * _lib.TC_TILE_N
         tile_elems = self.n_ntiles * self.n_ktiles * _lib.TILE_K * _lib.TILE_N
         self.R = torch.empty(tile_elems, dtype=torch.float32, device=dev)
         self.MB = torch.empty(tile_elems, dtype=torch.float32, device=dev)
@@ -73,9 +78,46 @@ class DenseIndex:
         _lib.check(L.cw_index_build(tree.store.struct(), self.order.data_ptr(), self.nn, C.byref(ix), _lib.stream_ptr()),
                    "cw_index_build")
         self._ws = None
+        self.tx = None
+        self.mode = "fp32"
+
+    def set_mode(self, mode):
+        """Select the scoring kernel for predict / predict_host / node_scores; builds the tensor-core
+        operands (cw_tc_index_build) on first use."""
+        if mode not in self.MODES:
+            raise ValueError(f"mode must be one of {self.MODES}")
+        if mode == "tf32x3" and self.tx is None:
+            L, dev, d = _lib.load(), self.tree.device, self.tree.d
+            tx = _lib.CwTcIndex()
+            tx.D, tx.nn = d, self.nn
+            tx.n_ntiles = (self.nn + _lib.TC_TILE_N - 1) // _lib.TC_TILE_N
+            tx.n_slabs = (d + _lib.TC_SLAB_D - 1) // _lib.TC_SLAB_D
+            self.tcB = torch.empty(L.cw_tc_b_bytes(self.nn, d), dtype=torch.uint8, device=dev)
+            self.hconst = torch.empty(tx.n_ntiles * _lib.TC_TILE_N, dtype=torch.float32, device=dev)
+            tx.B, tx.hconst = self.tcB.data_ptr(), self.hconst.data_ptr()
+            _lib.check(L.cw_tc_index_build(self.tree.store.struct(), self.order.data_ptr(), self.nn, self.sumlog.data_ptr(),
+                                           C.byref(tx), _lib.stream_ptr()), "cw_tc_index_build")
+            self.tx = tx
+        self.mode = mode
+        return self
+
+    def _tx_ref(self):
+        return C.byref(self.tx) if self.mode == "tf32x3" else None
+
+    def _node_scores_call(self, q, nq, ws):
+        L = _lib.load()
+        if self.mode == "tf32x3":
+            _lib.check(L.cw_dense_node_scores_tc(C.byref(self.tx), q.data_ptr(), nq, ws["xt"].data_ptr(),
+                                                 ws["scores"].data_ptr(), ws["ldq"], _lib.stream_ptr()), "cw_dense_node_scores_tc")
+        else:
+            _lib.check(L.cw_dense_node_scores(C.byref(self.ix), q.data_ptr(), nq, ws["xt"].data_ptr(),
+                                              ws["scores"].data_ptr(), ws["ldq"], _lib.stream_ptr()), "cw_dense_node_scores")
 
     def bytes(self):
-        return (self.R.numel() + self.MB.numel() + self.sumlog.numel()) * 4
+        b = (self.R.numel() + self.MB.numel() + self.sumlog.numel()) * 4
+        if self.tx is not None:
+            b += self.tcB.numel() + self.hconst.numel() * 4
+        return b
 
     def chunk_queries(self):
         return int(max(128, min(65535, self.SCORE_BUDGET_BYTES // (self.ld * 4)) // 128 * 128))
@@ -92,7 +134,9 @@ class DenseIndex:
         ws = dict(
             cap_q=nq, cap_k=k,
             q=torch.empty((nq, self.tree.d), dtype=torch.float32, device=dev),
-            xt=torch.empty(L.cw_xt_floats(nq, self.tree.d), dtype=torch.float32, device=dev),
+            # query operands: k-major tiles (FP32 kernel) or swizzled hi/lo images (tensor-core kernel)
+            xt=torch.empty(max(L.cw_xt_floats(nq, self.tree.d) * 4, L.cw_tc_a_bytes(nq, self.tree.d)), dtype=torch.uint8,
+                           device=dev),
             ldq=int(L.cw_score_ldq(nq)),
             scores=torch.empty((self.ld, int(L.cw_score_ldq(nq))), dtype=torch.float32, device=dev),  # node-major
             sid=torch.empty((nq, k), dtype=torch.int32, device=dev),
@@ -104,11 +148,9 @@ class DenseIndex:
 
     def node_scores(self, Q):
         """[nq, nn] node log-likelihood scores in index (BFS) order (CobwebWrapper.py:283-287)."""
-        L = _lib.load()
         nq = Q.shape[0]
         ws = self.workspace(nq, 0)
-        _lib.check(L.cw_dense_node_scores(C.byref(self.ix), Q.data_ptr(), nq, ws["xt"].data_ptr(), ws["scores"].data_ptr(),
-                                          ws["ldq"], _lib.stream_ptr()), "cw_dense_node_scores")
+        self._node_scores_call(Q, nq, ws)
         return ws["scores"][: self.nn, :nq].T
 
     def predict(self, Q, k, want_leaf_scores=False):
@@ -125,8 +167,7 @@ class DenseIndex:
             nq = min(step, nq_total - lo)
             ws = self.workspace(min(step, nq_total), k)
             q = Q[lo:lo + nq]
-            _lib.check(L.cw_dense_node_scores(C.byref(self.ix), q.data_ptr(), nq, ws["xt"].data_ptr(),
-                                              ws["scores"].data_ptr(), ws["ldq"], _lib.stream_ptr()), "cw_dense_node_scores")
+            self._node_scores_call(q, nq, ws)
             _lib.check(L.cw_dense_paths_topk(C.byref(self.ix), ws["scores"].data_ptr(), ws["ldq"], nq, k,
                                              leaf[lo:lo + nq].data_ptr() if leaf is not None else None,
                                              sids[lo:lo + nq].data_ptr(), vals[lo:lo + nq].data_ptr(),
@@ -146,7 +187,7 @@ class DenseIndex:
         for lo in range(0, nq_total, step):
             nq = min(step, nq_total - lo)
             ws = self.workspace(min(step, nq_total), k)
-            _lib.check(L.cw_predict_dense_host(C.byref(self.ix), Qh[lo:lo + nq].data_ptr(), nq, k, ws["q"].data_ptr(),
+            _lib.check(L.cw_predict_dense_host(C.byref(self.ix), self._tx_ref(), Qh[lo:lo + nq].data_ptr(), nq, k, ws["q"].data_ptr(),
                                                ws["xt"].data_ptr(), ws["scores"].data_ptr(), ws["ldq"], ws["sid"].data_ptr(),
                                                ws["val"].data_ptr(), ws["scratch"].data_ptr(),
                                                out_sid[lo:lo + nq].data_ptr(), out_val[lo:lo + nq].data_ptr(),
@@ -257,8 +298,21 @@ class CobwebWrapper:
         """CobwebWrapper.build_prediction_index (CobwebWrapper.py:91-208)."""
         if self._index is not None:
             return
-        self._index = DenseIndex(self.tree, self._leaf_of_sentence, self._level_weights)
+        self._index = DenseIndex(self.tree, self._leaf_of_sentence, self._level_weights).set_mode(self.dense_mode)
         self.max_depth = max(self.max_depth, self._index.max_depth)
+
+    dense_mode = "fp32"
+
+    def set_dense_mode(self, mode):
+        """Additive: where cobweb_predict_fast / predict_fast_batch compute node scores -- "fp32" (FP32 pipe,
+        default) or "tf32x3" (tcgen05 tensor cores, split-TF32 operands).  See DenseIndex.MODES."""
+        if mode not in DenseIndex.MODES:
+            raise ValueError(f"mode must be one of {DenseIndex.MODES}")
+        self.dense_mode = mode
+        if self._index is not None:
+            self._index.set_mode(mode)
+        if getattr(self, "_shard_index", None) is not None:
+            self._shard_index.set_mode(mode)
 
     def force_rebuild_index(self):
         self._invalidate_prediction_index()
@@ -327,7 +381,7 @@ class CobwebWrapper:
             tree_order = np.lexsort((np.arange(len(self._leaf_of_sentence)), row_of[self._leaf_of_sentence]))
             lo, hi = parallel.shard_bounds(len(tree_order), world, rank)
             self._shard_index = DenseIndex(self.tree, self._leaf_of_sentence, self._level_weights,
-                                           sentence_ids=np.sort(tree_order[lo:hi]))
+                                           sentence_ids=np.sort(tree_order[lo:hi])).set_mode(self.dense_mode)
             self._shard_key = key
         Q = self.tree._as_device_mat(Q)
         kk = min(int(k), self._shard_index.n_pos, _lib.MAX_K)
