@@ -16,13 +16,13 @@ CW_USE_INFO, CW_USE_KL, CW_ACUITY_CUTOFF = 1, 2, 4
 HDR_WORDS = 16
 SCRATCH_WORDS = 16384
 TILE_N, TILE_K, MAX_K, MAX_D, MAX_CHILDREN = 128, 16, 128, 4096, 2048
-TC_TILE_Q, TC_TILE_N, TC_SLAB_D = 128, 256, 16
+TC_TILE_Q, TC_TILE_N, TC_SLAB_D, RESCORE_MAX_KC = 128, 256, 16, 64
 IFIT_NODE_SLACK, IFIT_POOL_SLACK = 160, 16384
 
 EXPORTS = ["cw_version", "cw_last_error", "cw_store_init", "cw_ifit", "cw_set_ifit_cluster", "cw_categorize_ctas", "cw_categorize",
            "cw_index_build", "cw_xt_floats", "cw_score_ldq", "cw_dense_node_scores", "cw_topk_chunks", "cw_dense_paths_topk",
            "cw_predict_dense_host", "cw_tc_b_bytes", "cw_tc_a_bytes", "cw_tc_index_build",
-           "cw_dense_node_scores_tc", "cw_rank_scores_bwd", "cw_whiten", "cw_ffma_peak", "cw_ffma2_peak"]
+           "cw_dense_node_scores_tc", "cw_rescore_smem_bytes", "cw_rescore_rows_build", "cw_dense_rescore", "cw_rank_scores_bwd", "cw_whiten", "cw_ffma_peak", "cw_ffma2_peak"]
 
 
 class CwStore(C.Structure):
@@ -42,7 +42,15 @@ class CwIndex(C.Structure):
 
 class CwTcIndex(C.Structure):
     _fields_ = [("D", C.c_int32), ("nn", C.c_int32), ("n_ntiles", C.c_int32), ("n_slabs", C.c_int32),
-                ("B", C.c_void_p), ("hconst", C.c_void_p)]
+                ("B", C.c_void_p), ("hconst", C.c_void_p), ("rows", C.c_void_p), ("pos_of_sid", C.c_void_p),
+                ("hmax", C.c_float), ("lmax", C.c_float), ("wfac", C.c_float), ("eps_scale", C.c_float)]
+
+
+class CwDenseWork(C.Structure):
+    _fields_ = [("Q_dev", C.c_void_p), ("xt_scratch", C.c_void_p), ("node_scores", C.c_void_p), ("ldq", C.c_int64),
+                ("out_sid_dev", C.c_void_p), ("out_score_dev", C.c_void_p), ("scratch", C.c_void_p),
+                ("cand_sid", C.c_void_p), ("cand_score", C.c_void_p), ("fail", C.c_void_p), ("kc", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 class CobwebB200Error(RuntimeError):
@@ -79,8 +87,13 @@ def load():
     L.cw_topk_chunks.restype = i64
     L.cw_topk_chunks.argtypes = [i64]
     L.cw_dense_paths_topk.argtypes = [C.POINTER(CwIndex), vp, i64, i64, i32, vp, vp, vp, vp, vp]
-    L.cw_predict_dense_host.argtypes = [C.POINTER(CwIndex), C.POINTER(CwTcIndex), vp, i64, i32, vp, vp, vp, i64, vp, vp, vp, vp,
-                                        vp, vp]
+    L.cw_predict_dense_host.argtypes = [C.POINTER(CwIndex), C.POINTER(CwTcIndex), C.POINTER(CwStore), vp, i64, i32,
+                                        C.POINTER(CwDenseWork), vp, vp, C.POINTER(C.c_int32), vp]
+    L.cw_rescore_smem_bytes.restype = i64
+    L.cw_rescore_smem_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+    L.cw_rescore_rows_build.argtypes = [C.POINTER(CwStore), vp, C.c_int32, vp, vp]
+    L.cw_dense_rescore.argtypes = [C.POINTER(CwStore), C.POINTER(CwIndex), vp, vp, vp, i64, i32, vp, vp, i32, C.c_float,
+                                   C.c_float, C.c_float, C.c_float, vp, vp, vp, vp]
     L.cw_tc_b_bytes.restype = i64
     L.cw_tc_b_bytes.argtypes = [C.c_int32, C.c_int32]
     L.cw_tc_a_bytes.restype = i64

@@ -20,6 +20,7 @@ UNITS = [
     ("cw_index.cu", ["-fmad=false"]),
     ("cw_dense.cu", []),
     ("cw_tensor.cu", []),
+    ("cw_rescore.cu", ["-fmad=false"]),
     ("cw_whiten.cu", []),
     ("cw_grad.cu", []),
 ]

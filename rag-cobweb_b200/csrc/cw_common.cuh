@@ -68,6 +68,15 @@ __device__ __forceinline__ float var_of(float m2, float count, float prior, bool
     return v + prior;
 }
 
+// Operands of the FP32-pipe dense score, (x - mean)^2 / var = (x*r + mb)^2 (cw_index.cu builds them into the
+// index tiles, cw_rescore.cu re-derives them from the store rows; both must round identically)
+__device__ __forceinline__ void dense_operands(float mean, float m2, float count, float prior, bool cutoff, float &r,
+                                               float &mb) {
+    const float var = count > 0.0f ? var_of(m2, count, prior, cutoff) : prior;
+    r = 1.0f / sqrtf(var);
+    mb = -(mean * r);
+}
+
 // per-attribute transform whose differences / values the score sums use: log var for the
 // information-theoretic modes, 1/(2 sqrt(pi) sqrt(var)) for the expected-correct-guess mode
 __device__ __forceinline__ float tf_of(float v, int mode) {

@@ -243,6 +243,22 @@ __device__ __noinline__ void fill_weight_row(float *wl, const double *lw, int le
     for (int j = lane; j < len; j += 32) wl[j] = (float)(lw[j] / (double)len);
 }
 
+// 4-byte asynchronous copy global -> shared (LDGSTS): the prefetch ring of the path kernel
+__device__ __forceinline__ void cp_async4(float *dst, const float *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+constexpr int PF_DIST = 6, PF_RING = 8, PF_LEVELS = 3, PF_RECS = 64;
+struct __align__(16) PathRec {
+    int len, m, leaf, sid;  // path length, levels shared with the previous position, leaf row, sentence id
+    int par, gpar, pad0, pad1;  // rows of levels len-2 / len-3 when they are not shared
+};
+
 // grid (position chunks, groups of `wpb` query groups): warp = 32 queries (lane = query) x one
 // chunk of sentence positions.  Positions are in tree order, so consecutive paths share a
 // prefix (siblings differ only in the leaf); the index stores per position
@@ -252,7 +268,14 @@ __device__ __noinline__ void fill_weight_row(float *wl, const double *lw, int le
 // as a full root-to-leaf chain (bit-equal to torch.sparse.mm on the reference's side).  Each
 // level is one coalesced 128-byte read of the node-major score matrix.  Every lane keeps its
 // query's sorted top-k in shared memory ([rank][lane]) behind a register threshold.
-__global__ void __launch_bounds__(256, 5)
+//
+// The score reads are the kernel's only long-latency operations and each depends on the record of
+// its position, so they are software-pipelined: records are loaded 32 positions at a time (lane =
+// position, one block ahead) into a shared-memory ring, and the scores of the last three levels of
+// position p + PF_DIST are in flight (cp.async into a per-lane ring) while position p is consumed.
+// Deeper non-shared levels (an ancestor above the grandparent changed: ~1 position in 60) are read
+// on demand.
+__global__ void __launch_bounds__(256, 3)
 paths_topk_kernel(const float *__restrict__ ST, unsigned ldq, long long nq, int n_pos, int max_len,
                   const int *__restrict__ path_pm, const int4 *__restrict__ pos_rec,
                   const double *__restrict__ level_w, int k, float *leaf_scores, float *cand_s, int *cand_i,
@@ -261,13 +284,15 @@ paths_topk_kernel(const float *__restrict__ ST, unsigned ldq, long long nq, int 
     // level weights in binary64; the path weight of level j on a path of length len is
     // (float)(level_w[j] / len), the fp32 value the reference stores in its sparse path matrix
     double *lw = reinterpret_cast<double *>(pt_smem);  // [max_len]
-    float *wt = reinterpret_cast<float *>(lw + max_len);
-    const int wt_n = 0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    float *Ls = wt + wt_n + (size_t)warp * k * 32;                                                // [32 lanes][k]
-    int *Li = reinterpret_cast<int *>(wt + wt_n + (size_t)wpb * k * 32) + (size_t)warp * k * 32;  // [32 lanes][k]
-    float *St = wt + wt_n + (size_t)2 * wpb * k * 32 + (size_t)warp * max_len * 32;               // [max_len][32]
-    float *wl = wt + wt_n + (size_t)2 * wpb * k * 32 + (size_t)wpb * max_len * 32 + (size_t)warp * max_len;  // [max_len]
+    PathRec *recs = reinterpret_cast<PathRec *>(lw + ((max_len + 1) & ~1)) + (size_t)warp * PF_RECS;            // [PF_RECS]
+    float *wt = reinterpret_cast<float *>(reinterpret_cast<PathRec *>(lw + ((max_len + 1) & ~1)) + (size_t)wpb * PF_RECS);
+    float *ring = wt + (size_t)warp * (PF_RING * PF_LEVELS * 32);                                               // [PF_RING][PF_LEVELS][32]
+    wt += (size_t)wpb * (PF_RING * PF_LEVELS * 32);
+    float *Ls = wt + (size_t)warp * k * 32;                                                // [32 lanes][k]
+    int *Li = reinterpret_cast<int *>(wt + (size_t)wpb * k * 32) + (size_t)warp * k * 32;  // [32 lanes][k]
+    float *St = wt + (size_t)2 * wpb * k * 32 + (size_t)warp * max_len * 32;               // [max_len][32]
+    float *wl = wt + (size_t)2 * wpb * k * 32 + (size_t)wpb * max_len * 32 + (size_t)warp * max_len;  // [max_len]
     for (int i = threadIdx.x; i < max_len; i += blockDim.x) lw[i] = level_w[i];
     const float NEG_INF = -__int_as_float(0x7f800000);
     for (int i = lane; i < 32 * k; i += 32) { Ls[i] = NEG_INF; Li[i] = -1; }
@@ -279,24 +304,57 @@ paths_topk_kernel(const float *__restrict__ ST, unsigned ldq, long long nq, int 
     const float *col = ST + (qvalid ? q : g * 32);
     const int chunk = blockIdx.x;
     const int p0 = chunk * chunk_len, p1 = min(n_pos, p0 + chunk_len);
+    const int n = p1 - p0;
     float thr_s = NEG_INF;
     int thr_i = -1;
     int wl_len = -1;  // path length the per-warp weight row wl[] was computed for
-    // one position ahead: its record and its leaf-level score are in flight while the current
-    // position is processed (the leaf row is the one read that is new for almost every position)
-    const int4 *rec = pos_rec + p0;
-    int4 rc = rec[0];
-    float leaf_c = col[(size_t)(unsigned)rc.z * ldq];
-    for (int p = p0; p < p1; p++) {
-        int4 rn = rc;
-        float leaf_n = 0.0f;
-        ++rec;
-        if (p + 1 < p1) {
-            rn = rec[0];
-            leaf_n = col[(size_t)(unsigned)rn.z * ldq];
+
+    // record of position p0 + r (lane-parallel): the first position of a chunk recomputes its whole path
+    auto load_rec = [&](int r) {
+        PathRec R;
+        R.len = 0; R.m = 0; R.leaf = 0; R.sid = -1; R.par = 0; R.gpar = 0; R.pad0 = 0; R.pad1 = 0;
+        if (r < n) {
+            const int4 rc = pos_rec[p0 + r];
+            R.len = rc.x; R.m = r == 0 ? 0 : rc.y; R.leaf = rc.z; R.sid = rc.w;
+            const int *path = path_pm + (size_t)(p0 + r) * max_len;
+            if (R.m <= R.len - 2) R.par = path[R.len - 2];
+            if (R.m <= R.len - 3) R.gpar = path[R.len - 3];
         }
-        const int len = rc.x;
-        const int m = p == p0 ? 0 : rc.y;
+        return R;
+    };
+    auto prefetch = [&](int r) {  // scores of the last three non-shared levels of position p0 + r
+        if (r < n) {
+            const PathRec R = recs[r & (PF_RECS - 1)];
+            float *slot = ring + (r & (PF_RING - 1)) * (PF_LEVELS * 32) + lane;
+            if (R.m < R.len) cp_async4(slot, col + (size_t)(unsigned)R.leaf * ldq);
+            if (R.m <= R.len - 2) cp_async4(slot + 32, col + (size_t)(unsigned)R.par * ldq);
+            if (R.m <= R.len - 3) cp_async4(slot + 64, col + (size_t)(unsigned)R.gpar * ldq);
+        }
+        cp_async_commit();
+    };
+    recs[lane] = load_rec(lane);
+    recs[32 + lane] = load_rec(32 + lane);
+    __syncwarp();
+    for (int r = 0; r < PF_DIST; r++) prefetch(r);
+    PathRec nb;  // records of the block after the next one, in flight
+    nb.len = 0; nb.m = 0; nb.leaf = 0; nb.sid = -1; nb.par = 0; nb.gpar = 0; nb.pad0 = 0; nb.pad1 = 0;
+
+    for (int r = 0; r < n; r++) {
+        const int p = p0 + r;
+        // record ring = two blocks of 32 positions.  At the start of block B (r = 32 B): the records of block
+        // B+1, fetched one block ago, take the slots of the finished block B-1; the fetch of block B+2 is issued.
+        if ((r & 31) == 0) {
+            if (r > 0) {
+                recs[((r + 32) & (PF_RECS - 1)) + lane] = nb;
+                __syncwarp();
+            }
+            nb = load_rec(r + 64 + lane);
+        }
+        prefetch(r + PF_DIST);
+        cp_async_wait<PF_DIST>();
+        const PathRec R = recs[r & (PF_RECS - 1)];
+        const float *slot = ring + (r & (PF_RING - 1)) * (PF_LEVELS * 32) + lane;
+        const int len = R.len, m = R.m;
         if (len != wl_len) {  // rare: positions are sorted by depth, so len changes a handful of times per chunk
             __syncwarp();
             fill_weight_row(wl, lw, len, lane);
@@ -304,16 +362,24 @@ paths_topk_kernel(const float *__restrict__ ST, unsigned ldq, long long nq, int 
             __syncwarp();
         }
         float acc = m > 0 ? St[(m - 1) * 32 + lane] : 0.0f;
-        for (int j = m; j < len - 1; j++) {  // rare: the parent (or higher) changed as well
+        for (int j = m; j < len - 3; j++) {  // rare: an ancestor above the grandparent changed as well
             const int b = path_pm[(size_t)p * max_len + j];
             acc = __fmaf_rn(wl[j], col[(size_t)(unsigned)b * ldq], acc);
             St[j * 32 + lane] = acc;
         }
+        if (m <= len - 3) {
+            acc = __fmaf_rn(wl[len - 3], slot[64], acc);
+            St[(len - 3) * 32 + lane] = acc;
+        }
+        if (m <= len - 2) {
+            acc = __fmaf_rn(wl[len - 2], slot[32], acc);
+            St[(len - 2) * 32 + lane] = acc;
+        }
         if (m < len) {
-            acc = __fmaf_rn(wl[len - 1], leaf_c, acc);
+            acc = __fmaf_rn(wl[len - 1], slot[0], acc);
             St[(len - 1) * 32 + lane] = acc;
         }
-        const int sid = rc.w;
+        const int sid = R.sid;
         if (qvalid && leaf_scores) leaf_scores[q * n_pos + sid] = acc;
         // top-k: lanes whose candidate beats their query's k-th best are served one at a time by
         // the whole warp (lane r handles rank r of that query's list): no divergent shifting loops
@@ -380,8 +446,6 @@ paths_topk_kernel(const float *__restrict__ ST, unsigned ldq, long long nq, int 
             if (lane == L) { thr_s = new_thr_s; thr_i = new_thr_i; }
             __syncwarp();
         }
-        rc = rn;
-        leaf_c = leaf_n;
     }
     if (k > 0 && qvalid) {
         float *os = cand_s + (q * n_chunks + chunk) * k;
@@ -522,12 +586,22 @@ extern "C" int cw_dense_paths_topk(const cw_index *ix, const float *node_scores,
     }
     if (nq == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    // warps per CTA: per warp the per-lane top-k lists take k*256 bytes of shared memory and the
-    // partial-sum stack max_len*128 bytes
-    const size_t per_warp = (size_t)k * 256 + (size_t)ix->max_len * 132;
-    int wpb = (int)(98304 / per_warp);
-    if (wpb > 8) wpb = 8;
-    if (wpb < 1) wpb = 1;
+    // warps per CTA: per warp the per-lane top-k lists take k*256 bytes of shared memory, the partial-sum
+    // stack max_len*128 bytes, the record and prefetch rings 5 KB; pick the CTA size that keeps most warps per SM
+    const size_t per_warp = (size_t)k * 256 + (size_t)ix->max_len * 132 + PF_RECS * sizeof(PathRec) +
+                            (size_t)PF_RING * PF_LEVELS * 32 * sizeof(float);
+    const size_t fixed = (size_t)((ix->max_len + 1) & ~1) * sizeof(double);
+    int wpb = 1, best_warps = 0;
+    for (int c = 8; c >= 1; c--) {
+        const size_t blk = fixed + c * per_warp;
+        if (blk > 200 * 1024) continue;
+        const int warps = (int)((227 * 1024) / (blk + 1024)) * c;
+        if (warps > best_warps) { best_warps = warps; wpb = c; }
+    }
+    if (best_warps == 0) {
+        cw_set_error("cw_dense_paths_topk: k=%d with max_len=%d needs more shared memory than one CTA has", k, ix->max_len);
+        return CW_E_ARG;
+    }
     const long long groups = (nq + 31) / 32;
     const long long gblocks = (groups + wpb - 1) / wpb;
     if (gblocks > 65535) {
@@ -544,7 +618,7 @@ extern "C" int cw_dense_paths_topk(const cw_index *ix, const float *node_scores,
     const int n_chunks = (ix->n_pos + chunk_len - 1) / chunk_len;
     float *cand_s = reinterpret_cast<float *>(scratch);
     int *cand_i = scratch + (size_t)nq * n_chunks * (k > 0 ? k : 1);
-    const size_t smem = (size_t)ix->max_len * sizeof(double) + (size_t)wpb * per_warp;
+    const size_t smem = fixed + (size_t)wpb * per_warp;
     if (smem > 48 * 1024) {
         int rc = cw_check_cuda(cudaFuncSetAttribute(paths_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                     (int)smem),
@@ -559,29 +633,84 @@ extern "C" int cw_dense_paths_topk(const cw_index *ix, const float *node_scores,
     return cw_check_cuda(cudaGetLastError(), "cw_dense_paths_topk");
 }
 
-extern "C" int cw_predict_dense_host(const cw_index *ix, const cw_tc_index *tx, const float *Q_host, int64_t nq, int k,
-                                     float *Q_dev, float *xt_scratch, float *node_scores, int64_t ldq, int32_t *out_sid_dev, float *out_score_dev,
-                                     int32_t *scratch, int32_t *out_sid_host, float *out_score_host, void *stream) {
-    if (!ix || !Q_host || !Q_dev || !out_sid_host || !out_score_host || k < 1) {
+// FP32-pipe answer for nq queries already in Q_dev: scores, paths, top-k, results into the device buffers
+static int fp32_predict(const cw_index *ix, const cw_dense_work *w, int64_t nq, int k, void *stream) {
+    const int64_t ldq = cw_score_ldq(nq);
+    int rc = cw_dense_node_scores(ix, w->Q_dev, nq, reinterpret_cast<float *>(w->xt_scratch), w->node_scores, ldq, stream);
+    if (rc) return rc;
+    return cw_dense_paths_topk(ix, w->node_scores, ldq, nq, k, nullptr, w->out_sid_dev, w->out_score_dev, w->scratch, stream);
+}
+
+extern "C" int cw_predict_dense_host(const cw_index *ix, const cw_tc_index *tx, const cw_store *s, const float *Q_host,
+                                     int64_t nq, int k, const cw_dense_work *w, int32_t *out_sid_host,
+                                     float *out_score_host, int32_t *n_fallback, void *stream) {
+    if (!ix || !Q_host || !w || !w->Q_dev || !out_sid_host || !out_score_host || k < 1 ||
+        (tx && (!s || !w->cand_sid || !w->cand_score || !w->fail || w->kc <= k))) {
         cw_set_error("cw_predict_dense_host: bad argument");
         return CW_E_ARG;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = cw_check_cuda(cudaMemcpyAsync(Q_dev, Q_host, (size_t)nq * ix->D * sizeof(float), cudaMemcpyHostToDevice, st),
+    if (n_fallback) *n_fallback = 0;
+    const size_t row_i = (size_t)k * sizeof(int32_t), row_f = (size_t)k * sizeof(float);
+    int rc = cw_check_cuda(cudaMemcpyAsync(w->Q_dev, Q_host, (size_t)nq * ix->D * sizeof(float), cudaMemcpyHostToDevice, st),
                            "cw_predict_dense_host: H2D");
     if (rc) return rc;
-    rc = tx ? cw_dense_node_scores_tc(tx, Q_dev, nq, xt_scratch, node_scores, ldq, stream)
-            : cw_dense_node_scores(ix, Q_dev, nq, xt_scratch, node_scores, ldq, stream);
-    if (rc) return rc;
-    if ((rc = cw_dense_paths_topk(ix, node_scores, ldq, nq, k, nullptr, out_sid_dev, out_score_dev, scratch, stream)))
+    int32_t n_fail = 0;
+    if (tx) {  // tensor-core pre-filter + exact re-score
+        if ((rc = cw_dense_node_scores_tc(tx, w->Q_dev, nq, w->xt_scratch, w->node_scores, w->ldq, stream))) return rc;
+        if ((rc = cw_dense_paths_topk(ix, w->node_scores, w->ldq, nq, w->kc, nullptr, w->cand_sid, w->cand_score, w->scratch,
+                                      stream)))
+            return rc;
+        if ((rc = cw_dense_rescore(s, ix, tx->rows, tx->pos_of_sid, w->Q_dev, nq, w->kc, w->cand_sid, w->cand_score, k, tx->hmax,
+                                   tx->lmax, tx->wfac, tx->eps_scale, w->out_sid_dev, w->out_score_dev, w->fail, stream)))
+            return rc;
+        rc = cw_check_cuda(cudaMemcpyAsync(&n_fail, w->fail, sizeof(int32_t), cudaMemcpyDeviceToHost, st),
+                           "cw_predict_dense_host: D2H flag");
+        if (rc) return rc;
+    } else if ((rc = fp32_predict(ix, w, nq, k, stream))) {
         return rc;
-    rc = cw_check_cuda(cudaMemcpyAsync(out_sid_host, out_sid_dev, (size_t)nq * k * sizeof(int32_t),
-                                       cudaMemcpyDeviceToHost, st),
+    }
+    rc = cw_check_cuda(cudaMemcpyAsync(out_sid_host, w->out_sid_dev, (size_t)nq * row_i, cudaMemcpyDeviceToHost, st),
                        "cw_predict_dense_host: D2H ids");
     if (rc) return rc;
-    rc = cw_check_cuda(cudaMemcpyAsync(out_score_host, out_score_dev, (size_t)nq * k * sizeof(float),
-                                       cudaMemcpyDeviceToHost, st),
+    rc = cw_check_cuda(cudaMemcpyAsync(out_score_host, w->out_score_dev, (size_t)nq * row_f, cudaMemcpyDeviceToHost, st),
                        "cw_predict_dense_host: D2H scores");
     if (rc) return rc;
-    return cw_check_cuda(cudaStreamSynchronize(st), "cw_predict_dense_host: sync");
+    if ((rc = cw_check_cuda(cudaStreamSynchronize(st), "cw_predict_dense_host: sync"))) return rc;
+    if (n_fail == 0) return 0;
+
+    // flagged queries: answered on the FP32 pipe.  Few: their rows are compacted to the front of Q_dev (ascending,
+    // so no row is overwritten before it is moved) and scattered back; many: the whole batch is redone.
+    if (n_fallback) *n_fallback = n_fail;
+    if ((int64_t)n_fail * 4 > nq) {
+        rc = cw_check_cuda(cudaMemcpyAsync(w->Q_dev, Q_host, (size_t)nq * ix->D * sizeof(float), cudaMemcpyHostToDevice, st),
+                           "cw_predict_dense_host: H2D");
+        if (rc || (rc = fp32_predict(ix, w, nq, k, stream))) return rc;
+        cudaMemcpyAsync(out_sid_host, w->out_sid_dev, (size_t)nq * row_i, cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(out_score_host, w->out_score_dev, (size_t)nq * row_f, cudaMemcpyDeviceToHost, st);
+        return cw_check_cuda(cudaStreamSynchronize(st), "cw_predict_dense_host: fallback sync");
+    }
+    int32_t *list = new int32_t[n_fail];
+    rc = cw_check_cuda(cudaMemcpy(list, w->fail + 1, (size_t)n_fail * sizeof(int32_t), cudaMemcpyDeviceToHost),
+                       "cw_predict_dense_host: D2H flagged list");
+    if (!rc) {
+        for (int i = 1; i < n_fail; i++) {  // insertion sort, n_fail is small
+            const int32_t v = list[i];
+            int j = i - 1;
+            for (; j >= 0 && list[j] > v; j--) list[j + 1] = list[j];
+            list[j + 1] = v;
+        }
+        const size_t qrow = (size_t)ix->D * sizeof(float);
+        for (int i = 0; i < n_fail; i++)
+            if (list[i] != i)
+                cudaMemcpyAsync(w->Q_dev + (size_t)i * ix->D, w->Q_dev + (size_t)list[i] * ix->D, qrow, cudaMemcpyDeviceToDevice, st);
+        rc = fp32_predict(ix, w, n_fail, k, stream);
+        for (int i = 0; i < n_fail && !rc; i++) {
+            cudaMemcpyAsync(out_sid_host + (size_t)list[i] * k, w->out_sid_dev + (size_t)i * k, row_i, cudaMemcpyDeviceToHost, st);
+            cudaMemcpyAsync(out_score_host + (size_t)list[i] * k, w->out_score_dev + (size_t)i * k, row_f, cudaMemcpyDeviceToHost, st);
+        }
+        if (!rc) rc = cw_check_cuda(cudaStreamSynchronize(st), "cw_predict_dense_host: fallback sync");
+    }
+    delete[] list;
+    return rc;
 }

@@ -69,11 +69,8 @@ index_tiles_kernel(cw_store s, const int *__restrict__ order, int nn, int n_ktil
     for (int e = 0; e < KPT; e++) {
         const int kk = part * KPT + e, d = kt * CW_TILE_K + kk;
         float r = 0.0f, mb = 0.0f;
-        if (node >= 0 && d < D) {
-            float var = cnt > 0.0f ? var_of(s.m2[(size_t)node * D + d], cnt, prior, cutoff) : prior;
-            r = 1.0f / sqrtf(var);
-            mb = -(s.mean[(size_t)node * D + d] * r);
-        }
+        if (node >= 0 && d < D)
+            dense_operands(s.mean[(size_t)node * D + d], s.m2[(size_t)node * D + d], cnt, prior, cutoff, r, mb);
         tr[kk][nl] = r;
         tm[kk][nl] = mb;
     }

@@ -28,8 +28,11 @@ class DenseIndex:
 
     SCORE_BUDGET_BYTES = 8 << 30  # node-score scratch per query chunk
     # where the node scores are computed: "fp32" = FP32 pipe, (x*r + mb)^2 per triple (cw_dense.cu);
-    # "tf32x3" = tcgen05 contraction with hi/lo-split TF32 operands (cw_tensor.cu), ~1e-6 relative to "fp32"
+    # "tf32x3" = tcgen05 contraction with hi/lo-split TF32 operands (cw_tensor.cu, ~1e-6 relative to "fp32") as a
+    # pre-filter for top-kc candidates, followed by the exact re-score (cw_rescore.cu): top-k ids and scores are
+    # bit-identical to "fp32"; raw node / leaf score matrices in this mode are the approximate ones
     MODES = ("fp32", "tf32x3")
+    EPS_SCALE = 2.0 ** -18  # bound of |tf32x3 - fp32| leaf score relative to the operand magnitudes (cw_dense_rescore)
 
     def __init__(self, tree, leaf_of_sentence, level_weights=None, sentence_ids=None):
         """leaf_of_sentence[i] = leaf node id of sentence i.  sentence_ids (optional, sorted global
@@ -97,12 +100,28 @@ class DenseIndex:
             tx.B, tx.hconst = self.tcB.data_ptr(), self.hconst.data_ptr()
             _lib.check(L.cw_tc_index_build(self.tree.store.struct(), self.order.data_ptr(), self.nn, self.sumlog.data_ptr(),
                                            C.byref(tx), _lib.stream_ptr()), "cw_tc_index_build")
+            # constants of the re-score margin: hmax = max_b sum_d mean^2/var (= -2 h - sumlog), lmax = max_b |sumlog|,
+            # wfac = max over path lengths of sum_j |level_w[j]| / len
+            sl = self.sumlog[: self.nn].double()
+            tx.hmax = float((-2.0 * self.hconst[: self.nn].double() - sl).max().clamp_min(0.0)) * (1.0 + 1e-6) + 1e-6
+            tx.lmax = float(sl.abs().max())
+            tx.wfac, tx.eps_scale = 1.0, self.EPS_SCALE
+            if self.n_pos:
+                rec = self.pos_rec.cpu().numpy()
+                cw = np.cumsum(np.abs(self.level_w.cpu().numpy()))
+                lens = np.unique(rec[:, 0])
+                tx.wfac = float(max(1.0, (cw[lens - 1] / lens).max()))
+                pos_of_sid = np.full(int(rec[:, 3].max()) + 1, -1, np.int32)
+                pos_of_sid[rec[:, 3]] = np.arange(len(rec), dtype=np.int32)
+                self.pos_of_sid = torch.as_tensor(pos_of_sid, device=dev)
+                tx.pos_of_sid = self.pos_of_sid.data_ptr()
+            self.rows = torch.empty((self.nn, d, 2), dtype=torch.float32, device=dev)
+            _lib.check(L.cw_rescore_rows_build(self.tree.store.struct(), self.order.data_ptr(), self.nn, self.rows.data_ptr(),
+                                               _lib.stream_ptr()), "cw_rescore_rows_build")
+            tx.rows = self.rows.data_ptr()
             self.tx = tx
         self.mode = mode
         return self
-
-    def _tx_ref(self):
-        return C.byref(self.tx) if self.mode == "tf32x3" else None
 
     def _node_scores_call(self, q, nq, ws):
         L = _lib.load()
@@ -116,7 +135,7 @@ class DenseIndex:
     def bytes(self):
         b = (self.R.numel() + self.MB.numel() + self.sumlog.numel()) * 4
         if self.tx is not None:
-            b += self.tcB.numel() + self.hconst.numel() * 4
+            b += self.tcB.numel() + self.hconst.numel() * 4 + self.rows.numel() * 4
         return b
 
     def chunk_queries(self):
@@ -141,10 +160,32 @@ class DenseIndex:
             scores=torch.empty((self.ld, int(L.cw_score_ldq(nq))), dtype=torch.float32, device=dev),  # node-major
             sid=torch.empty((nq, k), dtype=torch.int32, device=dev),
             val=torch.empty((nq, k), dtype=torch.float32, device=dev),
-            scratch=torch.empty(max(1, nq * L.cw_topk_chunks(max(self.n_pos, 1)) * k * 2), dtype=torch.int32, device=dev),
         )
+        kc = max(k, self.candidates(k))
+        ws["scratch"] = torch.empty(max(1, nq * L.cw_topk_chunks(max(self.n_pos, 1)) * kc * 2), dtype=torch.int32, device=dev)
+        ws["cand_sid"] = torch.empty((nq, kc), dtype=torch.int32, device=dev)
+        ws["cand_val"] = torch.empty((nq, kc), dtype=torch.float32, device=dev)
+        ws["fail"] = torch.zeros(1 + nq, dtype=torch.int32, device=dev)
         self._ws = ws
         return ws
+
+    def candidates(self, k):
+        """Candidates per query the tensor-core pre-filter hands to the exact re-score (0 = this k is served by
+        the FP32 path: k too large, or paths too long for the re-score kernel's shared memory)."""
+        if k < 1 or k > 32 or not self.n_pos:
+            return 0
+        kc = max(32, 2 * k)
+        if kc * self.max_len > 65535 or _lib.load().cw_rescore_smem_bytes(self.tree.d, self.max_len, kc) > 200 * 1024:
+            return 0
+        return kc
+
+    def _work_struct(self, ws, k):
+        w = _lib.CwDenseWork()
+        w.Q_dev, w.xt_scratch, w.node_scores, w.ldq = ws["q"].data_ptr(), ws["xt"].data_ptr(), ws["scores"].data_ptr(), ws["ldq"]
+        w.out_sid_dev, w.out_score_dev, w.scratch = ws["sid"].data_ptr(), ws["val"].data_ptr(), ws["scratch"].data_ptr()
+        w.cand_sid, w.cand_score, w.fail = ws["cand_sid"].data_ptr(), ws["cand_val"].data_ptr(), ws["fail"].data_ptr()
+        w.kc = self.candidates(k)
+        return w
 
     def node_scores(self, Q):
         """[nq, nn] node log-likelihood scores in index (BFS) order (CobwebWrapper.py:283-287)."""
@@ -153,26 +194,61 @@ class DenseIndex:
         self._node_scores_call(Q, nq, ws)
         return ws["scores"][: self.nn, :nq].T
 
-    def predict(self, Q, k, want_leaf_scores=False):
-        """Device batch -> (sids [nq,k] int32, scores [nq,k], leaf_scores [nq,L] or None)."""
+    def predict(self, Q, k, want_leaf_scores=False, mode=None):
+        """Device batch -> (sids [nq,k] int32, scores [nq,k], leaf_scores [nq,L] or None).  mode overrides
+        self.mode for this call.  In "tf32x3" mode top-k goes pre-filter -> exact re-score -> FP32 answer for
+        flagged queries (self.n_fallback counts them); leaf_scores, if requested, come from the same node scores
+        as the top-k of that mode (approximate for "tf32x3")."""
         L = _lib.load()
         if want_leaf_scores and self.sentence_ids is not None:
             raise ValueError("leaf scores are indexed by global sentence id; not available on a sentence shard")
+        mode = mode or self.mode
+        if mode != self.mode:
+            prev = self.mode
+            self.set_mode(mode)
+            try:
+                return self.predict(Q, k, want_leaf_scores)
+            finally:
+                self.mode = prev
+        kc = self.candidates(k) if (mode == "tf32x3" and not want_leaf_scores) else 0
+        if mode == "tf32x3" and kc == 0 and k > 0 and not want_leaf_scores:
+            return self.predict(Q, k, mode="fp32")  # this k / depth is not served by the re-score kernel
         nq_total = Q.shape[0]
         step = self.chunk_queries()
         sids = torch.empty((nq_total, max(k, 1)), dtype=torch.int32, device=Q.device)
         vals = torch.empty((nq_total, max(k, 1)), dtype=torch.float32, device=Q.device)
         leaf = torch.empty((nq_total, self.n_pos), dtype=torch.float32, device=Q.device) if want_leaf_scores else None
+        redo = []
         for lo in range(0, nq_total, step):
             nq = min(step, nq_total - lo)
             ws = self.workspace(min(step, nq_total), k)
             q = Q[lo:lo + nq]
             self._node_scores_call(q, nq, ws)
-            _lib.check(L.cw_dense_paths_topk(C.byref(self.ix), ws["scores"].data_ptr(), ws["ldq"], nq, k,
-                                             leaf[lo:lo + nq].data_ptr() if leaf is not None else None,
-                                             sids[lo:lo + nq].data_ptr(), vals[lo:lo + nq].data_ptr(),
-                                             ws["scratch"].data_ptr(), _lib.stream_ptr()), "cw_dense_paths_topk")
+            if kc:
+                _lib.check(L.cw_dense_paths_topk(C.byref(self.ix), ws["scores"].data_ptr(), ws["ldq"], nq, kc, None,
+                                                 ws["cand_sid"].data_ptr(), ws["cand_val"].data_ptr(), ws["scratch"].data_ptr(),
+                                                 _lib.stream_ptr()), "cw_dense_paths_topk")
+                tx = self.tx
+                _lib.check(L.cw_dense_rescore(self.tree.store.struct(), C.byref(self.ix), tx.rows, tx.pos_of_sid, q.data_ptr(),
+                                              nq, kc, ws["cand_sid"].data_ptr(), ws["cand_val"].data_ptr(), k, tx.hmax, tx.lmax,
+                                              tx.wfac, tx.eps_scale, sids[lo:lo + nq].data_ptr(), vals[lo:lo + nq].data_ptr(),
+                                              ws["fail"].data_ptr(), _lib.stream_ptr()), "cw_dense_rescore")
+                nf = int(ws["fail"][0])  # one 4-byte read-back per chunk
+                if nf:
+                    redo.append(ws["fail"][1:1 + nf].long() + lo)
+            else:
+                _lib.check(L.cw_dense_paths_topk(C.byref(self.ix), ws["scores"].data_ptr(), ws["ldq"], nq, k,
+                                                 leaf[lo:lo + nq].data_ptr() if leaf is not None else None,
+                                                 sids[lo:lo + nq].data_ptr(), vals[lo:lo + nq].data_ptr(),
+                                                 ws["scratch"].data_ptr(), _lib.stream_ptr()), "cw_dense_paths_topk")
+        if redo:
+            idx = torch.cat(redo)
+            self.n_fallback += int(idx.numel())
+            s2, v2, _ = self.predict(Q[idx].contiguous(), k, mode="fp32")
+            sids[idx], vals[idx] = s2, v2
         return sids, vals, leaf
+
+    n_fallback = 0  # queries answered by the FP32 path because the re-score margin did not hold
 
     def predict_host(self, Q_host, k, out_sid=None, out_val=None):
         """Host batch (numpy / pinned tensor) -> host ids/scores through the single C-ABI call
@@ -184,14 +260,17 @@ class DenseIndex:
         if out_sid is None:
             out_sid = torch.empty((nq_total, k), dtype=torch.int32)
             out_val = torch.empty((nq_total, k), dtype=torch.float32)
+        tensor = self.mode == "tf32x3" and self.candidates(k) > 0
+        nfb = C.c_int32(0)
         for lo in range(0, nq_total, step):
             nq = min(step, nq_total - lo)
             ws = self.workspace(min(step, nq_total), k)
-            _lib.check(L.cw_predict_dense_host(C.byref(self.ix), self._tx_ref(), Qh[lo:lo + nq].data_ptr(), nq, k, ws["q"].data_ptr(),
-                                               ws["xt"].data_ptr(), ws["scores"].data_ptr(), ws["ldq"], ws["sid"].data_ptr(),
-                                               ws["val"].data_ptr(), ws["scratch"].data_ptr(),
-                                               out_sid[lo:lo + nq].data_ptr(), out_val[lo:lo + nq].data_ptr(),
+            w = self._work_struct(ws, k)
+            _lib.check(L.cw_predict_dense_host(C.byref(self.ix), C.byref(self.tx) if tensor else None,
+                                               self.tree.store.struct(), Qh[lo:lo + nq].data_ptr(), nq, k, C.byref(w),
+                                               out_sid[lo:lo + nq].data_ptr(), out_val[lo:lo + nq].data_ptr(), C.byref(nfb),
                                                _lib.stream_ptr()), "cw_predict_dense_host")
+            self.n_fallback += nfb.value
         return out_sid, out_val
 
 
@@ -200,7 +279,7 @@ class _RankScores(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, Q, index):
-        _, _, leaf = index.predict(Q.detach(), 0, want_leaf_scores=True)
+        _, _, leaf = index.predict(Q.detach(), 0, want_leaf_scores=True, mode="fp32")
         ctx.index = index
         ctx.save_for_backward(Q.detach())
         return leaf
@@ -355,7 +434,7 @@ class CobwebWrapper:
         Q = self.tree._as_device_mat(Q)
         k = min(int(k), self._index.n_pos)
         if k > _lib.MAX_K:
-            _, _, leaf = self._index.predict(Q, 0, want_leaf_scores=True)
+            _, _, leaf = self._index.predict(Q, 0, want_leaf_scores=True, mode="fp32")
             vals, ids = torch.sort(leaf, dim=1, descending=True, stable=True)
             return ids[:, :k].to(torch.int32), vals[:, :k]
         sids, vals, _ = self._index.predict(Q, k)
@@ -404,7 +483,7 @@ class CobwebWrapper:
             Qd = Q.to(device=self.device, dtype=torch.float32)
             Qd = Qd.reshape(1, -1) if Qd.dim() == 1 else Qd
             return _RankScores.apply(Qd.contiguous(), self._index)
-        _, _, leaf = self._index.predict(self.tree._as_device_mat(Q), 0, want_leaf_scores=True)
+        _, _, leaf = self._index.predict(self.tree._as_device_mat(Q), 0, want_leaf_scores=True, mode="fp32")
         return leaf
 
     def cobweb_predict_indexed(self, input, k=5, return_ids=False, is_embedding=False):

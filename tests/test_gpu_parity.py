@@ -459,3 +459,74 @@ def test_wrapper_input_conventions():
     assert 61 in w_np.cobweb_predict(extra[1], k=1, return_ids=True, is_embedding=True) and leaf.children == []
     info = w_np.get_weight_schedule_info()
     assert info["schedule_type"] is None and w_np.get_prediction_index_info()["index_valid"]
+
+
+@pytest.mark.parametrize("n,d,kind,k", [(700, 128, "unit", 10), (900, 256, "whitened", 5), (400, 1024, "unit", 10),
+                                        (300, 100, "unit", 3), (1500, 40, "whitened", 16), (600, 384, "unit", 32)])
+def test_tensor_core_predict_matches_fp32_path(n, d, kind, k):
+    """"tf32x3" dense predict (tcgen05 split-TF32 contraction -> top-kc candidates -> exact re-score,
+    cw_tensor.cu + cw_rescore.cu) returns the FP32-pipe path's ids AND scores bit for bit; its raw node
+    scores agree with the FP32 kernel and with the oracle (CobwebWrapper.py:283-287) far inside the 1e-4
+    relative bar of the contract."""
+    x = synth.corpus(n, d, kind, seed=3)
+    w = CobwebWrapper(corpus=[None] * n, corpus_embeddings=x)
+    q, _ = synth.queries(x, 333, kind, seed=4)  # not a multiple of the 128-query tile
+    qd = torch.from_numpy(q).cuda()
+    w.build_prediction_index()
+    ix = w._index
+    ns32 = ix.node_scores(qd).clone()
+    ids32, v32, _ = ix.predict(qd, k)
+    ix.set_mode("tf32x3")
+    nstc = ix.node_scores(qd).clone()
+    # tolerance: 1e-5 of the score plus the cancellation floor of the contraction form (operand magnitude T)
+    x2 = float((qd * qd).sum(1).max())
+    floor = 2.0 ** -18 * 2.0 * (x2 / w.tree.store.prior_var + ix.tx.hmax)
+    err = (nstc - ns32).abs()
+    assert bool((err <= 1e-5 * ns32.abs() + floor).all()), float(err.max())
+    ref = OracleTree(d)
+    ref.ifit(x)
+    ref.build_index()
+    rns, _ = ref.dense_scores(q[:64])
+    np.testing.assert_allclose(nstc[:64].cpu().numpy(), rns, rtol=1e-5, atol=floor + 8 * EPS32 * float(np.abs(rns).max()))
+    assert ix.candidates(k) in (32, 64)
+    before = ix.n_fallback
+    ids, vals, _ = ix.predict(qd, k)
+    assert torch.equal(ids, ids32) and torch.equal(vals, v32)
+    hs, hv = ix.predict_host(q, k)
+    assert np.array_equal(hs.numpy(), ids32.cpu().numpy()) and np.array_equal(hv.numpy(), v32.cpu().numpy())
+    assert ix.n_fallback - before <= 4  # the margin holds for (nearly) every query on continuous data
+    # reference-shaped API in tensor mode
+    w.set_dense_mode("tf32x3")
+    assert w.cobweb_predict_fast(q[0], k=k, return_ids=True, is_embedding=True) == list(ids32[0].cpu().numpy())
+
+
+def test_tensor_core_predict_fallback_paths():
+    """Flagged queries (duplicates: more equal-scoring sentences than candidates), k beyond the re-score
+    kernel's range, fewer sentences than candidates, a level-weight schedule: always the FP32 path's answer."""
+    rng = np.random.default_rng(5)
+    base = synth.corpus(40, 64, "unit", seed=6)
+    x = np.concatenate([np.repeat(base[:3], 50, axis=0), base[3:]]).astype(np.float32)  # 3 leaves with 50 sentences each
+    x = x[rng.permutation(len(x))]
+    w = CobwebWrapper(corpus=[None] * len(x), corpus_embeddings=x)
+    q = np.concatenate([base[:3] + 1e-3, synth.queries(x, 61, "unit", seed=7)[0]]).astype(np.float32)
+    qd = torch.from_numpy(q).cuda()
+    w.set_level_weights([1.0, 0.5, 2.0, 1.0, 0.25])
+    w.build_prediction_index()
+    ix = w._index
+    for k in (1, 10, 32, 40):
+        ix.set_mode("fp32")
+        ids32, v32, _ = ix.predict(qd, k)
+        ix.set_mode("tf32x3")
+        n0 = ix.n_fallback
+        ids, vals, _ = ix.predict(qd, k)
+        assert torch.equal(ids, ids32) and torch.equal(vals, v32), k
+        if k == 10:
+            assert ix.n_fallback - n0 >= 3  # the three duplicate-heavy queries cannot be decided from 32 candidates
+        hs, hv = ix.predict_host(q, k)
+        assert np.array_equal(hs.numpy(), ids32.cpu().numpy()) and np.array_equal(hv.numpy(), v32.cpu().numpy()), k
+    # fewer sentences than candidates
+    w2 = CobwebWrapper(corpus=[None] * 12, corpus_embeddings=base[:12])
+    w2.build_prediction_index()
+    a, b, _ = w2._index.predict(qd, 10)
+    c, e, _ = w2._index.set_mode("tf32x3").predict(qd, 10)
+    assert torch.equal(a, c) and torch.equal(b, e)

@@ -55,6 +55,11 @@ def main():
     dd = (stc - s32).abs()
     print(f"tf32x3 vs fp32 kernel, all {stc.numel()} scores: max abs {dd.max().item():.3e}, "
           f"max rel {(dd / s32.abs()).max().item():.3e}", flush=True)
+    print(f"re-score: candidates/query {ix.candidates(k)}, queries sent to the FP32 fallback {ix.n_fallback}; "
+          f"ids identical {bool((idstc == ids32).all())}, scores bit-identical {bool((vtc == v32).all())}", flush=True)
+    hs, hv = ix.predict_host(q, k)
+    print(f"host call: ids identical {bool((hs.cuda() == ids32).all())}, scores bit-identical {bool((hv.cuda() == v32).all())}, "
+          f"fallbacks so far {ix.n_fallback}", flush=True)
     same = (idstc == ids32).all(1).float().mean().item()
     sets = np.mean([len(set(a) & set(b)) / k for a, b in zip(idstc.cpu().numpy(), ids32.cpu().numpy())])
     rec32 = float(np.mean([t in g for t, g in zip(targets, ids32.cpu().numpy())]))
