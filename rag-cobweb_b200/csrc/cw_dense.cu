@@ -322,13 +322,16 @@ paths_topk_kernel(const float *__restrict__ ST, unsigned ldq, long long nq, int 
         }
         return R;
     };
-    auto prefetch = [&](int r) {  // scores of the last three non-shared levels of position p0 + r
+    auto prefetch = [&](int r) {  // scores of the last (up to three) non-shared levels of position p0 + r
         if (r < n) {
             const PathRec R = recs[r & (PF_RECS - 1)];
             float *slot = ring + (r & (PF_RING - 1)) * (PF_LEVELS * 32) + lane;
-            if (R.m < R.len) cp_async4(slot, col + (size_t)(unsigned)R.leaf * ldq);
-            if (R.m <= R.len - 2) cp_async4(slot + 32, col + (size_t)(unsigned)R.par * ldq);
-            if (R.m <= R.len - 3) cp_async4(slot + 64, col + (size_t)(unsigned)R.gpar * ldq);
+            const int nl = R.len - R.m;
+            if (nl >= 1) cp_async4(slot, col + (size_t)(unsigned)R.leaf * ldq);
+            if (nl >= 2) {
+                cp_async4(slot + 32, col + (size_t)(unsigned)R.par * ldq);
+                if (nl >= 3) cp_async4(slot + 64, col + (size_t)(unsigned)R.gpar * ldq);
+            }
         }
         cp_async_commit();
     };
@@ -337,48 +340,58 @@ paths_topk_kernel(const float *__restrict__ ST, unsigned ldq, long long nq, int 
     __syncwarp();
     for (int r = 0; r < PF_DIST; r++) prefetch(r);
     PathRec nb;  // records of the block after the next one, in flight
-    nb.len = 0; nb.m = 0; nb.leaf = 0; nb.sid = -1; nb.par = 0; nb.gpar = 0; nb.pad0 = 0; nb.pad1 = 0;
+    // The common position differs from its predecessor in the leaf only: its score is one FMA on top of the
+    // partial sum through the parent level, kept in a register together with the leaf-level weight.
+    float base = 0.0f, wleaf = 0.0f, last_acc = 0.0f;
 
-    for (int r = 0; r < n; r++) {
-        const int p = p0 + r;
-        // record ring = two blocks of 32 positions.  At the start of block B (r = 32 B): the records of block
-        // B+1, fetched one block ago, take the slots of the finished block B-1; the fetch of block B+2 is issued.
-        if ((r & 31) == 0) {
-            if (r > 0) {
-                recs[((r + 32) & (PF_RECS - 1)) + lane] = nb;
-                __syncwarp();
-            }
-            nb = load_rec(r + 64 + lane);
-        }
+    // record ring = two blocks of 32 positions.  At the start of block B: the records of block B+1, fetched one
+    // block ago, take the slots of the finished block B-1, and the fetch of block B+2 is issued.
+    for (int rb = 0; rb < n; rb += 32) {
+      if (rb > 0) {
+          recs[((rb + 32) & (PF_RECS - 1)) + lane] = nb;
+          __syncwarp();
+      }
+      nb = load_rec(rb + 64 + lane);
+      const int re = min(n, rb + 32);
+      for (int r = rb; r < re; r++) {
         prefetch(r + PF_DIST);
         cp_async_wait<PF_DIST>();
         const PathRec R = recs[r & (PF_RECS - 1)];
         const float *slot = ring + (r & (PF_RING - 1)) * (PF_LEVELS * 32) + lane;
         const int len = R.len, m = R.m;
-        if (len != wl_len) {  // rare: positions are sorted by depth, so len changes a handful of times per chunk
-            __syncwarp();
-            fill_weight_row(wl, lw, len, lane);
-            wl_len = len;
-            __syncwarp();
+        float acc;
+        if (m == len - 1 && len == wl_len) {
+            acc = __fmaf_rn(wleaf, slot[0], base);
+        } else if (m == len && len == wl_len) {  // another sentence of the previous position's leaf
+            acc = last_acc;
+        } else {
+            // levels m .. len-2 changed (or the path length did, then m = 0): rebuild the partial sums
+            const int p = p0 + r;
+            if (len != wl_len) {  // rare: positions are sorted by depth, so len changes a handful of times per chunk
+                __syncwarp();
+                fill_weight_row(wl, lw, len, lane);
+                wl_len = len;
+                __syncwarp();
+            }
+            float a = m > 0 ? St[(m - 1) * 32 + lane] : 0.0f;
+            for (int j = m; j < len - 3; j++) {  // rare: an ancestor above the grandparent changed as well
+                const int b = path_pm[(size_t)p * max_len + j];
+                a = __fmaf_rn(wl[j], col[(size_t)(unsigned)b * ldq], a);
+                St[j * 32 + lane] = a;
+            }
+            if (m <= len - 3) {
+                a = __fmaf_rn(wl[len - 3], slot[64], a);
+                St[(len - 3) * 32 + lane] = a;
+            }
+            if (m <= len - 2) {
+                a = __fmaf_rn(wl[len - 2], slot[32], a);
+                St[(len - 2) * 32 + lane] = a;
+            }
+            base = a;
+            wleaf = wl[len - 1];
+            acc = __fmaf_rn(wleaf, slot[0], base);
         }
-        float acc = m > 0 ? St[(m - 1) * 32 + lane] : 0.0f;
-        for (int j = m; j < len - 3; j++) {  // rare: an ancestor above the grandparent changed as well
-            const int b = path_pm[(size_t)p * max_len + j];
-            acc = __fmaf_rn(wl[j], col[(size_t)(unsigned)b * ldq], acc);
-            St[j * 32 + lane] = acc;
-        }
-        if (m <= len - 3) {
-            acc = __fmaf_rn(wl[len - 3], slot[64], acc);
-            St[(len - 3) * 32 + lane] = acc;
-        }
-        if (m <= len - 2) {
-            acc = __fmaf_rn(wl[len - 2], slot[32], acc);
-            St[(len - 2) * 32 + lane] = acc;
-        }
-        if (m < len) {
-            acc = __fmaf_rn(wl[len - 1], slot[0], acc);
-            St[(len - 1) * 32 + lane] = acc;
-        }
+        last_acc = acc;
         const int sid = R.sid;
         if (qvalid && leaf_scores) leaf_scores[q * n_pos + sid] = acc;
         // top-k: lanes whose candidate beats their query's k-th best are served one at a time by
@@ -446,6 +459,7 @@ paths_topk_kernel(const float *__restrict__ ST, unsigned ldq, long long nq, int 
             if (lane == L) { thr_s = new_thr_s; thr_i = new_thr_i; }
             __syncwarp();
         }
+      }
     }
     if (k > 0 && qvalid) {
         float *os = cand_s + (q * n_chunks + chunk) * k;
@@ -608,9 +622,11 @@ extern "C" int cw_dense_paths_topk(const cw_index *ix, const float *node_scores,
         cw_set_error("cw_dense_paths_topk: too many queries per call (%lld)", (long long)nq);
         return CW_E_ARG;
     }
-    // aim for ~32 warps per SM (the kernel is issue-bound, and each chunk pays k ln(n/k) top-k
-    // insertions per query): few large chunks for big batches, many small ones for one query
-    long long want = (148 * 32 + groups - 1) / groups;
+    // one full wave of CTAs: (CTAs per SM at this shared-memory size) x SMs, split over the query-group blocks;
+    // each chunk pays k ln(n/k) top-k insertions per query, so no more chunks than that
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    long long want = (long long)sms * (best_warps / wpb) / gblocks;
     const long long max_chunks = cw_topk_chunks(ix->n_pos);
     if (want > max_chunks) want = max_chunks;
     if (want < 1) want = 1;

@@ -62,8 +62,6 @@ rescore_kernel(const RescoreArgs a) {
     unsigned short *slot = firstc + EMAX;                                   // [E]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool cutoff = (a.s.flags & CW_ACUITY_CUTOFF) != 0;
-    const float prior = a.s.prior_var;
     const int4 *pos_rec = reinterpret_cast<const int4 *>(a.ix.pos_rec);
     for (int i = tid; i < ML; i += RS_THREADS) lw[i] = a.ix.level_w[i];
 
