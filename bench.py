@@ -202,8 +202,10 @@ def _run_engine(args, wl):
         w._invalidate_prediction_index()
         torch.cuda.synchronize()
         log(f"[bench] rank {rank}: store broadcast {time.time() - t0:.2f}s")
+    w.set_dense_mode(args.mode)
     w.build_prediction_index()
     ix = w._index
+    tensor = args.mode == "tf32x3" and ix.candidates(k) > 0
     # this rank's batch: global batch = world * qn, contiguous shards
     q_all, targets_all = synth.queries(x, qn * world, kind, seed=1, targets=np.arange(qn * world) % docs)
     lo, hi = parallel.shard_bounds(qn * world, world, rank)
@@ -212,7 +214,9 @@ def _run_engine(args, wl):
     out_sid_h = torch.empty((qn, k), dtype=torch.int32).pin_memory()
     out_val_h = torch.empty((qn, k), dtype=torch.float32).pin_memory()
     chunks = (qn + ix.chunk_queries() - 1) // ix.chunk_queries()
-    launches_per_step = 4 * chunks
+    # kernels per chunk: tensor mode = query operands, tcgen05 scores, paths/top-kc, merge, re-score;
+    # FP32 mode = query tiles, FFMA scores, paths/top-k, merge
+    launches_per_step = (5 if tensor else 4) * chunks
 
     store_mode = args.shard == "store" and world > 1
     if store_mode:
@@ -266,6 +270,38 @@ def _run_engine(args, wl):
     ix.node_scores(q_dev[:nq_k])
     ms_kernel = timed(lambda: ix.node_scores(q_dev[:nq_k]), max(args.steps, 5)) / max(args.steps, 5)
     clocks = sampler.stop() if rank == 0 else None
+    n_fallback = ix.n_fallback
+
+    # the other scoring mode on the same batch: FP32-pipe kernel and whole step, and the identity of the results
+    fp32 = None
+    if tensor:
+        ids_t, vals_t, _ = ix.predict(q_dev, k)
+        ix.set_mode("fp32")
+        ids_f, vals_f, _ = ix.predict(q_dev, k)
+        ms_dev32 = timed(lambda: ix.predict(q_dev, k), 3) / 3
+        ms_k32 = timed(lambda: ix.node_scores(q_dev[:nq_k]), 3) / 3
+        ix.set_mode("tf32x3")
+        fp32 = {"queries_per_s": qn / (ms_dev32 * 1e-3), "ms_per_step": ms_dev32, "score_kernel_ms": ms_k32,
+                "ids_identical": bool(torch.equal(ids_t, ids_f)), "scores_bit_identical": bool(torch.equal(vals_t, vals_f))}
+
+    # TF32 tensor-pipe peak measured live: cuBLAS TF32 GEMM 8192^3, best of 5 (MEASURED_PEAKS.json has bf16 only)
+    tf32_peak = None
+    if tensor:
+        torch.backends.cuda.matmul.allow_tf32 = True
+        a = torch.randn(8192, 8192, device="cuda")
+        b = torch.randn(8192, 8192, device="cuda")
+        torch.matmul(a, b)
+        best = 1e9
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        tf32_peak = 2.0 * 8192 ** 3 / (best * 1e-3) / 1e12
+        torch.backends.cuda.matmul.allow_tf32 = False
+        del a, b
 
     # FP32-FMA issue peak measured the same way (back-to-back FFMA chains, CUDA events, best of 5)
     L = _lib.load()
@@ -346,9 +382,32 @@ def _run_engine(args, wl):
         tj = json.load(open(tp))
         if tj["workload"] == {"docs": docs, "dim": dim, "queries": nq_k}:
             traffic = tj["dense_score_kernel"]["dram_bytes_read"] + tj["dense_score_kernel"]["dram_bytes_write"]
-    flops = 4.0 * nq_k * nn * dim  # two FFMAs per (query, node, attribute)
+    flops = 4.0 * nq_k * nn * dim  # two FMAs per (query, node, attribute) in either form
     alg_bytes = 8.0 * nn * dim + 4.0 * nn + 4.0 * nq_k * dim + 4.0 * nq_k * nn
     achieved = flops / (ms_kernel * 1e-3) / 1e12
+    if tensor:
+        tj = os.path.join(ROOT, "profiles", "traffic_cfg3_tc.json")
+        traffic = None
+        if os.path.exists(tj):
+            t = json.load(open(tj))
+            if t["workload"] == {"docs": docs, "dim": dim, "queries": nq_k}:
+                traffic = t["tc_score_kernel"]["dram_bytes_read"] + t["tc_score_kernel"]["dram_bytes_write"]
+        peak = peaks["bf16_tflops"] / 2.0
+        roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                    "traffic": traffic, "algorithmic_bytes": alg_bytes, "kernel": "tc_score_kernel", "kernel_ms": ms_kernel,
+                    "flops_per_launch": flops,
+                    "peak_source": f"TF32 dense = half of the bf16 burst peak, {peak_src}",
+                    "executed_tflops": 3.0 * achieved, "executed_frac": 3.0 * achieved / peak,
+                    "executed_note": "every product is hi*hi + hi*lo + lo*hi of split-TF32 operands: 3 tcgen05.mma per algorithmic "
+                                     "MMA, so frac <= 1/3 by construction; executed_frac is the tensor-pipe utilisation",
+                    "tf32_cublas_tflops": tf32_peak,
+                    "hbm_frac": alg_bytes / (ms_kernel * 1e-3) / 1e9 / peaks["hbm_gbs"], "hbm_peak_source": peak_src}
+    else:
+        roofline = {"bound": "fp32", "achieved": achieved, "peak": ffma, "unit": "TFLOP/s", "frac": achieved / ffma,
+                    "traffic": traffic, "algorithmic_bytes": alg_bytes, "kernel": "dense_score_kernel", "kernel_ms": ms_kernel,
+                    "flops_per_launch": flops, "peak_source": "FFMA issue peak measured in this run (cw_ffma_peak)",
+                    "hbm_frac": alg_bytes / (ms_kernel * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                    "hbm_peak_source": peak_src}
     total_q = qn if store_mode else qn * world
     line = {
         "metric": "cobweb_predict_fast queries/sec", "value": total_q * args.steps / (ms_dev * 1e-3), "unit": "queries/s",
@@ -358,19 +417,20 @@ def _run_engine(args, wl):
         "config": {"workload": cfg, "docs": docs, "dim": dim, "nodes": nn, "queries_per_gpu": qn, "k": k,
                    "parallelism": (f"store sharded x{world} (sentences + ancestor nodes), NCCL all-gather + top-k merge"
                                    if store_mode else f"replicated store, query-sharded x{world}") if world > 1 else "single GPU",
-                   "l2": "inputs exceed L2 (node matrices %.0f MB per pass)" % (8.0 * nn * dim / 1e6)},
+                   "l2": "inputs exceed L2 (node matrices %.0f MB per pass)" % (8.0 * nn * dim / 1e6),
+                   "scoring": ("tf32x3: tcgen05 split-TF32 pre-filter (top-%d candidates) + exact FP32 re-score; ids and scores "
+                               "bit-identical to the FP32-pipe path" % ix.candidates(k)) if tensor else "fp32: FP32-pipe FFMA2 kernel"},
         "e2e": {"value": total_q * args.steps / (ms_host * 1e-3), "unit": "queries/s",
                 "h2d_bytes_per_step": int(qn * dim * 4), "d2h_bytes_per_step": int(qn * k * 8),
                 "api": "cw_predict_dense_host (C ABI, pinned host buffers)"},
         "gpu_launches": launches_per_step * args.steps,
-        "roofline": {"bound": "fp32", "achieved": achieved, "peak": ffma, "unit": "TFLOP/s", "frac": achieved / ffma,
-                     "traffic": traffic, "algorithmic_bytes": alg_bytes, "kernel": "dense_score_kernel", "kernel_ms": ms_kernel,
-                     "flops_per_launch": flops, "peak_source": "FFMA issue peak measured in this run (cw_ffma_peak)",
-                     "hbm_frac": alg_bytes / (ms_kernel * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                     "hbm_peak_source": peak_src},
+        "roofline": roofline,
         "cpu_baseline": cpu,
         "clocks": clocks,
         "recall_at_k": recall,
+        "fp32_path": fp32,
+        "ffma_peak_tflops": ffma,
+        "fallback_queries": n_fallback,
         "best_first": {"queries_per_s": nbf * world / (ms_bf * 1e-3), "rows_scored_per_query": bf_rows,
                        "queries": nbf, "hbm_frac": nbf * bf_rows * (8.0 * dim + 4) / (ms_bf * 1e-3) / 1e9 / peaks["hbm_gbs"],
                        "note": "cobweb_predict semantics (CobwebTorchTree._cobweb_categorize), algorithmic bytes = rows scored x (8D+4)"},
@@ -394,6 +454,9 @@ def main():
     ap.add_argument("--docs", type=int)
     ap.add_argument("--queries", type=int)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="tf32x3", choices=["tf32x3", "fp32"],
+                    help="node scores on the tensor cores (tcgen05 split-TF32 pre-filter + exact FP32 re-score, default) "
+                         "or on the FP32 pipe; the results are identical")
     ap.add_argument("--shard", default="query", choices=["query", "store"],
                     help="N>1: 'query' replicates the store and shards the batch (weak scaling, default); "
                          "'store' shards sentences+nodes, every rank answers the whole batch, per-rank top-k "

@@ -275,6 +275,7 @@ struct __align__(16) PathRec {
 // position p + PF_DIST are in flight (cp.async into a per-lane ring) while position p is consumed.
 // Deeper non-shared levels (an ancestor above the grandparent changed: ~1 position in 60) are read
 // on demand.
+template <bool LEAF, bool K32>
 __global__ void __launch_bounds__(256, 3)
 paths_topk_kernel(const float *__restrict__ ST, unsigned ldq, long long nq, int n_pos, int max_len,
                   const int *__restrict__ path_pm, const int4 *__restrict__ pos_rec,
@@ -305,8 +306,11 @@ paths_topk_kernel(const float *__restrict__ ST, unsigned ldq, long long nq, int 
     const int chunk = blockIdx.x;
     const int p0 = chunk * chunk_len, p1 = min(n_pos, p0 + chunk_len);
     const int n = p1 - p0;
+    // k-th best of this lane's query so far; while the list is not full: (-inf, INT_MAX), which every finite
+    // candidate beats (sentence ids compare as unsigned, so the empty id -1 also loses every tie)
     float thr_s = NEG_INF;
-    int thr_i = -1;
+    int thr_i = 0x7fffffff;
+    const bool collect = k > 0 && qvalid;
     int wl_len = -1;  // path length the per-warp weight row wl[] was computed for
 
     // record of position p0 + r (lane-parallel): the first position of a chunk recomputes its whole path
@@ -393,11 +397,11 @@ paths_topk_kernel(const float *__restrict__ ST, unsigned ldq, long long nq, int 
         }
         last_acc = acc;
         const int sid = R.sid;
-        if (qvalid && leaf_scores) leaf_scores[q * n_pos + sid] = acc;
+        if (LEAF && qvalid) leaf_scores[q * n_pos + sid] = acc;
         // top-k: lanes whose candidate beats their query's k-th best are served one at a time by
         // the whole warp (lane r handles rank r of that query's list): no divergent shifting loops
-        unsigned need = __ballot_sync(0xffffffffu, k > 0 && qvalid && cand_better(acc, sid, thr_s, thr_i));
-        if (k <= 32) {
+        unsigned need = __ballot_sync(0xffffffffu, collect && (acc > thr_s || (acc == thr_s && (unsigned)sid < (unsigned)thr_i)));
+        if (K32) {
             // one rank per lane: read, ballot the insertion point, shift by one, done
             while (need) {
                 const int L = __ffs(need) - 1;
@@ -417,11 +421,12 @@ paths_topk_kernel(const float *__restrict__ ST, unsigned ldq, long long nq, int 
                     const bool cand_last = (k < 2) || (pos == k - 1);
                     thr_s = cand_last ? cv : ps;
                     thr_i = cand_last ? sid : pi;
+                    if (thr_i < 0) thr_i = 0x7fffffff;  // list not full yet
                 }
                 __syncwarp();
             }
         }
-        while (need) {
+        while (!K32 && need) {
             const int L = __ffs(need) - 1;
             need &= need - 1;
             const float cv = __shfl_sync(0xffffffffu, acc, L);
@@ -456,7 +461,7 @@ paths_topk_kernel(const float *__restrict__ ST, unsigned ldq, long long nq, int 
                     if (pos < k - 1) { new_thr_s = ps; new_thr_i = pi; }
                 }
             }
-            if (lane == L) { thr_s = new_thr_s; thr_i = new_thr_i; }
+            if (lane == L) { thr_s = new_thr_s; thr_i = new_thr_i < 0 ? 0x7fffffff : new_thr_i; }
             __syncwarp();
         }
       }
@@ -635,13 +640,14 @@ extern "C" int cw_dense_paths_topk(const cw_index *ix, const float *node_scores,
     float *cand_s = reinterpret_cast<float *>(scratch);
     int *cand_i = scratch + (size_t)nq * n_chunks * (k > 0 ? k : 1);
     const size_t smem = fixed + (size_t)wpb * per_warp;
+    auto kern = leaf_scores ? (k <= 32 ? paths_topk_kernel<true, true> : paths_topk_kernel<true, false>)
+                            : (k <= 32 ? paths_topk_kernel<false, true> : paths_topk_kernel<false, false>);
     if (smem > 48 * 1024) {
-        int rc = cw_check_cuda(cudaFuncSetAttribute(paths_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                    (int)smem),
+        int rc = cw_check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                                "cw_dense_paths_topk: smem attribute");
         if (rc) return rc;
     }
-    paths_topk_kernel<<<dim3(n_chunks, (unsigned)gblocks), wpb * 32, smem, st>>>(
+    kern<<<dim3(n_chunks, (unsigned)gblocks), wpb * 32, smem, st>>>(
         node_scores, (unsigned)ldq, nq, ix->n_pos, ix->max_len, ix->path_idx, reinterpret_cast<const int4 *>(ix->pos_rec),
         ix->level_w, k, leaf_scores, cand_s, cand_i, n_chunks, chunk_len);
     if (k > 0)
