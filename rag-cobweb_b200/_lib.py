@@ -16,7 +16,7 @@ CW_USE_INFO, CW_USE_KL, CW_ACUITY_CUTOFF = 1, 2, 4
 HDR_WORDS = 16
 SCRATCH_WORDS = 16384
 TILE_N, TILE_K, MAX_K, MAX_D, MAX_CHILDREN = 128, 16, 128, 4096, 2048
-TC_TILE_Q, TC_TILE_N, TC_SLAB_D, RESCORE_MAX_KC = 128, 256, 16, 64
+TC_TILE_Q, TC_TILE_N, TC_SLAB_D, RESCORE_MAX_KC = 256, 256, 8, 64
 IFIT_NODE_SLACK, IFIT_POOL_SLACK = 160, 16384
 
 EXPORTS = ["cw_version", "cw_last_error", "cw_store_init", "cw_ifit", "cw_set_ifit_cluster", "cw_categorize_ctas", "cw_categorize",

@@ -13,16 +13,22 @@
 // TMEM) per K step; the dropped lo*lo term is below 2^-22 relative.  Measured against the
 // FP32-pipe kernel (cw_dense.cu) the node scores agree to ~1e-6 relative (tests/test_gpu_parity.py).
 //
-// Kernel shape: persistent, one CTA per SM, 192 threads:
-//   warp 0   producer: cp.async.bulk (TMA bulk copy) of one 96 KB stage = {A_hi, A_lo} 128 queries x 32
-//            features + {B_hi, B_lo} 256 nodes x 32 features; the operands are stored in HBM as
-//            the exact shared-memory image (K-major rows of 128 bytes, 128-byte swizzle), so a
-//            stage is two contiguous copies and needs no tensor map;
-//   warp 1   MMA issuer: one lane issues 12 tcgen05.mma (M=128, N=256, K=8) per stage and
-//            tcgen05.commit's the stage back to the producer / the accumulator to the epilogue;
-//   warps 2-5 epilogue: tcgen05.ld of the 128x256 fp32 accumulator (lane = query, column =
-//            node), h[n] - 0.5*acc, written NODE-major (one 128-byte line per warp store);
-// two accumulators (2 x 256 TMEM columns) so the epilogue of tile t overlaps the MMAs of t+1.
+// Kernel shape: persistent, one CTA per SM, 192 threads, CTA tile = 256 queries x 256 nodes:
+//   warp 0   producer: cp.async.bulk (TMA bulk copy) of one 64 KB stage = {A_hi, A_lo} 256 queries x 16
+//            features + {B_hi, B_lo} 256 nodes x 16 features (8 attributes: 8 "x^2 | 1/var" then 8
+//            "x | -2 mean/var"); the operands are stored in HBM as the exact shared-memory image
+//            (K-major rows of 64 bytes, 64-byte swizzle), so a stage is two contiguous copies and
+//            needs no tensor map; 3 stages;
+//   warp 1   MMA issuer: one lane issues 12 tcgen05.mma (M=128, N=256, K=8: two query halves x two K
+//            steps x three products) per stage and tcgen05.commit's the stage back to the producer /
+//            the accumulators to the epilogue;
+//   warps 2-5 epilogue: tcgen05.ld of the two 128x256 fp32 accumulators (lane = query, column =
+//            node; together all 512 TMEM columns), h[n] - 0.5*acc, written NODE-major (one 128-byte
+//            line per warp store).
+// Per stage a CTA moves 64 KB for 12 MMAs (1536 tensor cycles), 43 B/clk: the first version (128 x 256
+// tile, 96 KB per 12 MMAs) ran into the L2 throughput cap at 77 % tensor utilisation
+// (profiles/r01_tc_score_v1_ncu_full.md).  Tiles are enumerated in panels of query tiles (node tile
+// outer, query tile inner) so that the panel's query operands stay in L2 while the node operands stream.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -33,20 +39,21 @@ int cw_check_cuda(cudaError_t e, const char *what);
 
 namespace cwt {
 
-constexpr int TM = CW_TC_TILE_Q;     // queries per tile  (UMMA M)
+constexpr int TQ = CW_TC_TILE_Q;     // queries per CTA tile (two UMMA M = 128 halves)
+constexpr int TM = 128;              // UMMA M
 constexpr int TN = CW_TC_TILE_N;     // nodes per tile    (UMMA N)
 constexpr int SD = CW_TC_SLAB_D;     // attributes per K slab
-constexpr int ROWB = 128;            // bytes per operand row in a slab (32 tf32)
-constexpr int A_IMG = TM * ROWB;     // 16 KB
-constexpr int B_IMG = TN * ROWB;     // 32 KB
+constexpr int ROWB = 64;             // bytes per operand row in a slab (16 tf32)
+constexpr int A_IMG = TQ * ROWB;     // 16 KB
+constexpr int B_IMG = TN * ROWB;     // 16 KB
 constexpr int A_BYTES = 2 * A_IMG;   // hi + lo
 constexpr int B_BYTES = 2 * B_IMG;
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;  // 96 KB
-constexpr int NSTAGE = 2;
-constexpr int NACC = 2;
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;  // 64 KB
+constexpr int NSTAGE = 3;
 constexpr int THREADS = 192;
 constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
-static_assert(SD * 2 * 4 == ROWB, "a slab row is 16 x^2 features + 16 x features");
+static_assert(SD * 2 * 4 == ROWB, "a slab row is 8 x^2 features + 8 x features");
+static_assert(TQ == 2 * TM, "two accumulators per CTA tile");
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -103,14 +110,14 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uin
         : "memory");
 }
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp): K-major operand,
-// rows of 128 bytes, 128-byte swizzle; 8-row groups 1024 bytes apart.
+// rows of 64 bytes, 64-byte swizzle (Swizzle<2,4,3>); 8-row groups 512 bytes apart.
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);  // start address, 16-byte units
     d |= (uint64_t)1 << 16;                    // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset between 8-row groups
+    d |= (uint64_t)(8 * ROWB >> 4) << 32;      // stride byte offset between 8-row groups
     d |= (uint64_t)1 << 46;                    // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+    d |= (uint64_t)4 << 61;                    // SWIZZLE_64B
     return d;
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, M x N
@@ -140,20 +147,33 @@ __device__ __forceinline__ void split_tf32(float v, float &hi, float &lo) {
     lo = __uint_as_float(l);
 }
 
-// byte offset of 16-byte chunk c (0..7) of row r inside a 128-byte-swizzled operand image
-__device__ __forceinline__ int swz_off(int r, int c) { return r * ROWB + ((c ^ (r & 7)) << 4); }
+// byte offset of 16-byte chunk c (0..3) of row r inside a 64-byte-swizzled operand image: address bits [7,9)
+// (row / 2 within the 8-row group) are XORed into the chunk bits [4,6)
+__device__ __forceinline__ int swz_off(int r, int c) { return r * ROWB + ((c ^ ((r >> 1) & 3)) << 4); }
 
 // ------------------------------------------------------------------ the scoring kernel
+// tile t -> (node tile, query tile): panels of pq query tiles, node tile outer / query tile inner within a panel
+__device__ __forceinline__ void tile_coords(long long t, int n_qtiles, int n_ntiles, int pq, int &nt, int &qt) {
+    const long long per_full = (long long)pq * n_ntiles;
+    const int n_panels = (n_qtiles + pq - 1) / pq;
+    int p = (int)(t / per_full);
+    if (p > n_panels - 1) p = n_panels - 1;
+    const long long rem = t - (long long)p * per_full;
+    const int w = min(pq, n_qtiles - p * pq);
+    nt = (int)(rem / w);
+    qt = p * pq + (int)(rem % w);
+}
+
 __global__ void __launch_bounds__(THREADS, 1)
 tc_score_kernel(const unsigned char *__restrict__ A, const unsigned char *__restrict__ B,
                 const float *__restrict__ hconst, float *__restrict__ out, long long ldq, int n_qtiles, int n_ntiles,
-                int n_slabs) {
+                int n_slabs, int pq) {
     extern __shared__ unsigned char smem_raw[];
-    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // swizzle atoms need 1024-byte alignment
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // swizzle atoms need their natural alignment
     const uint32_t bars = base + NSTAGE * STAGE_BYTES;
-    // barrier words: full[NSTAGE], empty[NSTAGE], acc_full[NACC], acc_empty[NACC], then the TMEM base address
-    const uint32_t full0 = bars, empty0 = bars + 8 * NSTAGE, accf0 = bars + 16 * NSTAGE, acce0 = accf0 + 8 * NACC;
-    const uint32_t tmem_slot = acce0 + 8 * NACC;
+    // barrier words: full[NSTAGE], empty[NSTAGE], acc_full, acc_empty, then the TMEM base address
+    const uint32_t full0 = bars, empty0 = bars + 8 * NSTAGE, accf = bars + 16 * NSTAGE, acce = accf + 8;
+    const uint32_t tmem_slot = acce + 8;
     uint32_t *tmem_slot_ptr = reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -162,10 +182,8 @@ tc_score_kernel(const unsigned char *__restrict__ A, const unsigned char *__rest
             mbar_init(full0 + 8 * s, 1);
             mbar_init(empty0 + 8 * s, 1);
         }
-        for (int a = 0; a < NACC; a++) {
-            mbar_init(accf0 + 8 * a, 1);
-            mbar_init(acce0 + 8 * a, 4);  // one arrival per epilogue warp
-        }
+        mbar_init(accf, 1);
+        mbar_init(acce, 4);  // one arrival per epilogue warp
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {  // TMEM: all 512 columns (two 128 x 256 fp32 accumulators); this warp also frees them
@@ -185,7 +203,8 @@ tc_score_kernel(const unsigned char *__restrict__ A, const unsigned char *__rest
             int stage = 0;
             uint32_t phase = 0;
             for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-                const int nt = (int)(t / n_qtiles), qt = (int)(t % n_qtiles);
+                int nt, qt;
+                tile_coords(t, n_qtiles, n_ntiles, pq, nt, qt);
                 const unsigned char *asrc = A + (size_t)qt * n_slabs * A_BYTES;
                 const unsigned char *bsrc = B + (size_t)nt * n_slabs * B_BYTES;
                 for (int s = 0; s < n_slabs; s++) {
@@ -203,60 +222,69 @@ tc_score_kernel(const unsigned char *__restrict__ A, const unsigned char *__rest
         // ===== MMA issuer
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc(TM, TN);
-            int stage = 0, acc = 0;
+            int stage = 0;
             uint32_t phase = 0, aphase = 0;
             for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-                mbar_wait(acce0 + 8 * acc, aphase ^ 1);  // epilogue has drained this accumulator
+                mbar_wait(acce, aphase ^ 1);  // epilogue has drained the accumulators of the previous tile
                 tc_fence_after();
-                const uint32_t d = tmem_base + (uint32_t)(acc * TN);
                 for (int s = 0; s < n_slabs; s++) {
                     mbar_wait(full0 + 8 * stage, phase);
                     tc_fence_after();
                     const uint32_t sb = base + stage * STAGE_BYTES;
-                    const uint64_t a_hi = make_smem_desc(sb), a_lo = make_smem_desc(sb + A_IMG);
                     const uint64_t b_hi = make_smem_desc(sb + A_BYTES), b_lo = make_smem_desc(sb + A_BYTES + B_IMG);
 #pragma unroll
-                    for (int k = 0; k < ROWB / 32; k++) {  // 8 TF32 = 32 bytes per MMA; +2 in 16-byte address units
-                        const uint64_t ko = (uint64_t)(2 * k);
-                        tc_mma_tf32(d, a_hi + ko, b_hi + ko, idesc, (s | k) != 0);
-                        tc_mma_tf32(d, a_hi + ko, b_lo + ko, idesc, 1);
-                        tc_mma_tf32(d, a_lo + ko, b_hi + ko, idesc, 1);
+                    for (int qh = 0; qh < 2; qh++) {  // the two 128-query halves of the tile, one accumulator each
+                        const uint32_t d = tmem_base + (uint32_t)(qh * TN);
+                        const uint64_t a_hi = make_smem_desc(sb + qh * (TM * ROWB));
+                        const uint64_t a_lo = make_smem_desc(sb + A_IMG + qh * (TM * ROWB));
+#pragma unroll
+                        for (int k = 0; k < ROWB / 32; k++) {  // 8 TF32 = 32 bytes per MMA; +2 in 16-byte address units
+                            const uint64_t ko = (uint64_t)(2 * k);
+                            tc_mma_tf32(d, a_hi + ko, b_hi + ko, idesc, (s | k) != 0);
+                            tc_mma_tf32(d, a_hi + ko, b_lo + ko, idesc, 1);
+                            tc_mma_tf32(d, a_lo + ko, b_hi + ko, idesc, 1);
+                        }
                     }
                     tc_commit(empty0 + 8 * stage);  // stage free once these MMAs have read it
-                    if (s == n_slabs - 1) tc_commit(accf0 + 8 * acc);
+                    if (s == n_slabs - 1) tc_commit(accf);
                     if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                 }
-                if (++acc == NACC) { acc = 0; aphase ^= 1; }
+                aphase ^= 1;
             }
         }
         __syncwarp();
     } else {
-        // ===== epilogue: warp w reads TMEM lanes 32*(w%4) .. +31 (lane = query of the tile)
+        // ===== epilogue: warp w reads TMEM lanes 32*(w%4) .. +31 (lane = query of the 128-query half)
         const int quarter = warp & 3;
-        int acc = 0;
         uint32_t aphase = 0;
         for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-            const int nt = (int)(t / n_qtiles), qt = (int)(t % n_qtiles);
-            mbar_wait(accf0 + 8 * acc, aphase);
+            int nt, qt;
+            tile_coords(t, n_qtiles, n_ntiles, pq, nt, qt);
+            mbar_wait(accf, aphase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * TN);
-            float *col = out + (long long)qt * TM + quarter * 32 + lane;
             const long long n0 = (long long)nt * TN;
 #pragma unroll 1
-            for (int c = 0; c < TN / 32; c++) {
-                uint32_t v[32];
-                CW_TMEM_LD32(taddr + (uint32_t)(c * 32), v);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            for (int qh = 0; qh < 2; qh++) {
+                const long long q0 = (long long)qt * TQ + qh * TM;
+                if (q0 >= ldq) break;  // a half-tile of pure padding past the score matrix
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(qh * TN);
+                float *col = out + q0 + quarter * 32 + lane;
+#pragma unroll 1
+                for (int c = 0; c < TN / 32; c++) {
+                    uint32_t v[32];
+                    CW_TMEM_LD32(taddr + (uint32_t)(c * 32), v);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                for (int j = 0; j < 32; j++) {
-                    const long long n = n0 + c * 32 + j;
-                    col[n * ldq] = fmaf(-0.5f, __uint_as_float(v[j]), __ldg(hconst + n));
+                    for (int j = 0; j < 32; j++) {
+                        const long long n = n0 + c * 32 + j;
+                        col[n * ldq] = fmaf(-0.5f, __uint_as_float(v[j]), __ldg(hconst + n));
+                    }
                 }
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(acce0 + 8 * acc);
-            if (++acc == NACC) { acc = 0; aphase ^= 1; }
+            if (lane == 0) mbar_arrive(acce);
+            aphase ^= 1;
         }
     }
 
@@ -269,30 +297,33 @@ tc_score_kernel(const unsigned char *__restrict__ A, const unsigned char *__rest
 }
 
 // ------------------------------------------------------------------ operand builders
-// Queries: Q [nq, D] -> A [q tile][slab][hi, lo][128 rows x 128 B swizzled]; row = (x^2 x16 | x x16)
+// Queries: Q [nq, D] -> A [q tile][slab][hi, lo][256 rows x 64 B swizzled]; row = (x^2 x8 | x x8)
 __global__ void __launch_bounds__(256)
 tc_queries_kernel(const float *__restrict__ Q, long long nq, int D, int n_slabs, unsigned char *A) {
-    const int qt = blockIdx.x, s = blockIdx.y, tid = threadIdx.x;
-    const int r = tid >> 1, half = tid & 1;  // half 0: squares, half 1: the values
-    const long long q = (long long)qt * TM + r;
+    const int qt = blockIdx.x, s = blockIdx.y, r = threadIdx.x;
+    const long long q = (long long)qt * TQ + r;
     unsigned char *img = A + ((size_t)qt * n_slabs + s) * A_BYTES;
+    float x[SD];
 #pragma unroll
-    for (int c4 = 0; c4 < 4; c4++) {
+    for (int e = 0; e < SD; e++) {
+        const int d = s * SD + e;
+        x[e] = (q < nq && d < D) ? Q[q * D + d] : 0.0f;
+    }
+#pragma unroll
+    for (int c = 0; c < 4; c++) {  // chunks 0,1: squares; chunks 2,3: the values
         float hi[4], lo[4];
 #pragma unroll
         for (int e = 0; e < 4; e++) {
-            const int d = s * SD + c4 * 4 + e;
-            float x = (q < nq && d < D) ? Q[q * D + d] : 0.0f;
-            if (half == 0) x = x * x;
-            split_tf32(x, hi[e], lo[e]);
+            const float v = x[(c & 1) * 4 + e];
+            split_tf32(c < 2 ? v * v : v, hi[e], lo[e]);
         }
-        const int off = swz_off(r, half * 4 + c4);
+        const int off = swz_off(r, c);
         *reinterpret_cast<float4 *>(img + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
         *reinterpret_cast<float4 *>(img + A_IMG + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
     }
 }
 
-// Nodes: B [node tile][slab][hi, lo][256 rows x 128 B swizzled]; row = (1/var x16 | -2 mean/var x16)
+// Nodes: B [node tile][slab][hi, lo][256 rows x 64 B swizzled]; row = (1/var x8 | -2 mean/var x8)
 __global__ void __launch_bounds__(256)
 tc_nodes_kernel(cw_store s, const int *__restrict__ order, int nn, int n_slabs, unsigned char *B) {
     const int nt = blockIdx.x, sl = blockIdx.y, r = threadIdx.x;
@@ -304,31 +335,31 @@ tc_nodes_kernel(cw_store s, const int *__restrict__ order, int nn, int n_slabs, 
     float cnt = 0.0f;
     if (b < nn) { node = order[b]; cnt = s.count[node]; }
     unsigned char *img = B + ((size_t)nt * n_slabs + sl) * B_BYTES;
+    float iv[SD], mv[SD];
 #pragma unroll
-    for (int c4 = 0; c4 < 4; c4++) {
-        float ihi[4], ilo[4], mhi[4], mlo[4];
-#pragma unroll
-        for (int e = 0; e < 4; e++) {
-            const int d = sl * SD + c4 * 4 + e;
-            float iv = 0.0f, mv = 0.0f;
-            if (node >= 0 && d < D) {
-                float var = prior;
-                if (cnt > 0.0f) {
-                    const float v = s.m2[(size_t)node * D + d] / cnt;  // CobwebTorchTree.compute_var
-                    var = cutoff ? (v < prior ? prior : v) : v + prior;
-                }
-                const double inv = 1.0 / (double)var;
-                iv = (float)inv;
-                mv = (float)(-2.0 * (double)s.mean[(size_t)node * D + d] * inv);
+    for (int e = 0; e < SD; e++) {
+        const int d = sl * SD + e;
+        iv[e] = 0.0f;
+        mv[e] = 0.0f;
+        if (node >= 0 && d < D) {
+            float var = prior;
+            if (cnt > 0.0f) {
+                const float v = s.m2[(size_t)node * D + d] / cnt;  // CobwebTorchTree.compute_var
+                var = cutoff ? (v < prior ? prior : v) : v + prior;
             }
-            split_tf32(iv, ihi[e], ilo[e]);
-            split_tf32(mv, mhi[e], mlo[e]);
+            const double inv = 1.0 / (double)var;
+            iv[e] = (float)inv;
+            mv[e] = (float)(-2.0 * (double)s.mean[(size_t)node * D + d] * inv);
         }
-        const int o1 = swz_off(r, c4), o2 = swz_off(r, 4 + c4);
-        *reinterpret_cast<float4 *>(img + o1) = make_float4(ihi[0], ihi[1], ihi[2], ihi[3]);
-        *reinterpret_cast<float4 *>(img + B_IMG + o1) = make_float4(ilo[0], ilo[1], ilo[2], ilo[3]);
-        *reinterpret_cast<float4 *>(img + o2) = make_float4(mhi[0], mhi[1], mhi[2], mhi[3]);
-        *reinterpret_cast<float4 *>(img + B_IMG + o2) = make_float4(mlo[0], mlo[1], mlo[2], mlo[3]);
+    }
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        float hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) split_tf32(c < 2 ? iv[(c & 1) * 4 + e] : mv[(c & 1) * 4 + e], hi[e], lo[e]);
+        const int off = swz_off(r, c);
+        *reinterpret_cast<float4 *>(img + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4 *>(img + B_IMG + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
     }
 }
 
@@ -364,7 +395,7 @@ tc_hconst_kernel(cw_store s, const int *__restrict__ order, int nn, int n_rows, 
 using namespace cwt;
 
 extern "C" int64_t cw_tc_a_bytes(int64_t nq, int32_t D) {
-    return ((nq + TM - 1) / TM) * (int64_t)((D + SD - 1) / SD) * A_BYTES;
+    return ((nq + TQ - 1) / TQ) * (int64_t)((D + SD - 1) / SD) * A_BYTES;
 }
 extern "C" int64_t cw_tc_b_bytes(int32_t nn, int32_t D) {
     return (int64_t)((nn + TN - 1) / TN) * (int64_t)((D + SD - 1) / SD) * B_BYTES;
@@ -393,7 +424,7 @@ extern "C" int cw_dense_node_scores_tc(const cw_tc_index *tx, const float *Q, in
     }
     if (nq == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    const int n_qtiles = (int)((nq + TM - 1) / TM);
+    const int n_qtiles = (int)((nq + TQ - 1) / TQ);
     int rc = cw_check_cuda(cudaFuncSetAttribute(tc_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES),
                            "cw_dense_node_scores_tc: smem attribute");
     if (rc) return rc;
@@ -403,8 +434,15 @@ extern "C" int cw_dense_node_scores_tc(const cw_tc_index *tx, const float *Q, in
                                                                   reinterpret_cast<unsigned char *>(a_scratch));
     const long long n_tiles = (long long)n_qtiles * tx->n_ntiles;
     const int grid = (int)(n_tiles < sms ? n_tiles : sms);
+    // query-tile panels: the panel's query operands (A_BYTES per tile and slab) should sit in L2 (~40 MB of it)
+    // while the node operands stream through; equal-width panels
+    const long long a_tile = (long long)tx->n_slabs * A_BYTES;
+    int pq_max = (int)((40ll << 20) / a_tile);
+    if (pq_max < 1) pq_max = 1;
+    const int n_panels = (n_qtiles + pq_max - 1) / pq_max;
+    const int pq = (n_qtiles + n_panels - 1) / n_panels;
     tc_score_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(reinterpret_cast<const unsigned char *>(a_scratch),
                                                        reinterpret_cast<const unsigned char *>(tx->B), tx->hconst,
-                                                       node_scores, ldq, n_qtiles, tx->n_ntiles, tx->n_slabs);
+                                                       node_scores, ldq, n_qtiles, tx->n_ntiles, tx->n_slabs, pq);
     return cw_check_cuda(cudaGetLastError(), "cw_dense_node_scores_tc");
 }
