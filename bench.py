@@ -401,6 +401,10 @@ def _run_engine(args, wl):
                     "executed_note": "every product is hi*hi + hi*lo + lo*hi of split-TF32 operands: 3 tcgen05.mma per algorithmic "
                                      "MMA, so frac <= 1/3 by construction; executed_frac is the tensor-pipe utilisation",
                     "tf32_cublas_tflops": tf32_peak,
+                    "tensor_pipe_tflops_at_clock": 148 * 4096 * (clocks["sm_mhz"] or 0) * 1e6 / 1e12 if clocks else None,
+                    "pipe_note": "tensor_pipe_tflops_at_clock = 148 SMs x 2048 TF32 FMA/clk x the SM clock sampled under load: the "
+                                 "hardware rate the executed MMAs run against (ncu: tensor pipe 90 % active, "
+                                 "profiles/r01_tc_score_v2_ncu_full.md); the measured cuBLAS figures are power-limited GEMMs",
                     "hbm_frac": alg_bytes / (ms_kernel * 1e-3) / 1e9 / peaks["hbm_gbs"], "hbm_peak_source": peak_src}
     else:
         roofline = {"bound": "fp32", "achieved": achieved, "peak": ffma, "unit": "TFLOP/s", "frac": achieved / ffma,
