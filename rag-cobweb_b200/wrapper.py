@@ -174,7 +174,9 @@ class DenseIndex:
         the FP32 path: k too large, or paths too long for the re-score kernel's shared memory)."""
         if k < 1 or k > 32 or not self.n_pos:
             return 0
-        kc = max(32, 2 * k)
+        # enough that the weakest candidate sits below (k-th best) - 2 eps: at cfg3 the gap between ranks 10 and 24
+        # is >= 3x that margin for every query (tools/tc_gap_probe.py); k-lists of up to 32 use the fast insertion path
+        kc = 24 if k <= 10 else (32 if k <= 16 else 2 * k)
         if kc * self.max_len > 65535 or _lib.load().cw_rescore_smem_bytes(self.tree.d, self.max_len, kc) > 200 * 1024:
             return 0
         return kc

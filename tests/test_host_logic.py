@@ -227,3 +227,36 @@ def test_query_sharding_world_size_2_gloo():
     port = _free_port()
     mp.spawn(_worker, args=(world, port, q, ret), nprocs=world, join=True)
     assert dict(ret) == {0: (True, True), 1: (True, True)}
+
+
+def test_evaluator_matches_the_reference_loop():
+    """metrics_from_ids == the reference's per-query loop (benchmark_utils.py:794-820, transcribed here with
+    sklearn's ndcg_score called the way the reference calls it), including short result lists."""
+    from sklearn.metrics import ndcg_score
+    from rag_cobweb_b200.evaluate import get_eval_ks, metrics_from_ids
+    rng = np.random.default_rng(0)
+    nq, top_k, n_docs = 300, 20, 60
+    retrieved = np.stack([rng.permutation(n_docs)[:top_k] for _ in range(nq)])
+    retrieved[5, 7:] = -1   # fewer than top_k documents came back
+    retrieved[6, 1:] = -1
+    targets = rng.integers(0, n_docs, nq)
+    targets[:40] = retrieved[:40, 0]  # some first-rank hits
+    ks = get_eval_ks(top_k)
+    assert ks == [2, 3, 5, 10, 20]
+    want = {f"{m}@{k}": 0.0 for k in ks for m in ("recall", "mrr", "ndcg")}
+    for row, target in zip(retrieved, targets):
+        docs = [d for d in row.tolist() if d >= 0]
+        for k in ks:
+            top = docs[:k]
+            if target in top:
+                want[f"recall@{k}"] += 1
+                want[f"mrr@{k}"] += 1 / (top.index(target) + 1)
+            relevance = [1 if d == target else 0 for d in top]
+            if sum(relevance) > 0 and len(relevance) > 1:
+                want[f"ndcg@{k}"] += ndcg_score([sorted(relevance, reverse=True)], [relevance])
+            elif sum(relevance) > 0:
+                want[f"ndcg@{k}"] += 1.0  # sklearn rejects single-document lists; the only document is the hit
+    got = metrics_from_ids("x", retrieved, targets, top_k, seconds=1.5)
+    for key, v in want.items():
+        assert got[key] == round(v / nq, 4), key
+    assert got["method"] == "x" and got["time_taken"] == 1.5 and got["avg_latency_ms"] == 5.0
