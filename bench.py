@@ -270,7 +270,7 @@ def _run_engine(args, wl):
     ix.node_scores(q_dev[:nq_k])
     ms_kernel = timed(lambda: ix.node_scores(q_dev[:nq_k]), max(args.steps, 5)) / max(args.steps, 5)
     clocks = sampler.stop() if rank == 0 else None
-    n_fallback = ix.n_fallback
+    n_fallback, n_escalated = ix.n_fallback, ix.n_escalated
 
     # the other scoring mode on the same batch: FP32-pipe kernel and whole step, and the identity of the results
     fp32 = None
@@ -434,7 +434,8 @@ def _run_engine(args, wl):
         "recall_at_k": recall,
         "fp32_path": fp32,
         "ffma_peak_tflops": ffma,
-        "fallback_queries": n_fallback,
+        "escalated_queries": n_escalated, "fallback_queries": n_fallback,
+        "queries_answered": int(qn * (2 * max(args.warmup, 3) + 2 * args.steps)),
         "best_first": {"queries_per_s": nbf * world / (ms_bf * 1e-3), "rows_scored_per_query": bf_rows,
                        "queries": nbf, "hbm_frac": nbf * bf_rows * (8.0 * dim + 4) / (ms_bf * 1e-3) / 1e9 / peaks["hbm_gbs"],
                        "note": "cobweb_predict semantics (CobwebTorchTree._cobweb_categorize), algorithmic bytes = rows scored x (8D+4)"},

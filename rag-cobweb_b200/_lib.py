@@ -50,7 +50,7 @@ class CwDenseWork(C.Structure):
     _fields_ = [("Q_dev", C.c_void_p), ("xt_scratch", C.c_void_p), ("node_scores", C.c_void_p), ("ldq", C.c_int64),
                 ("out_sid_dev", C.c_void_p), ("out_score_dev", C.c_void_p), ("scratch", C.c_void_p),
                 ("cand_sid", C.c_void_p), ("cand_score", C.c_void_p), ("fail", C.c_void_p), ("kc", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("kc2", C.c_int32)]
 
 
 class CobwebB200Error(RuntimeError):

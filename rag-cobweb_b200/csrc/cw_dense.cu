@@ -663,74 +663,103 @@ static int fp32_predict(const cw_index *ix, const cw_dense_work *w, int64_t nq, 
     return cw_dense_paths_topk(ix, w->node_scores, ldq, nq, k, nullptr, w->out_sid_dev, w->out_score_dev, w->scratch, stream);
 }
 
+// Tensor-core answer for nq queries already in Q_dev: pre-filter scores, top-kc candidates, exact re-score;
+// flagged queries are listed in w->fail
+static int tensor_predict(const cw_index *ix, const cw_tc_index *tx, const cw_store *s, const cw_dense_work *w, int64_t nq,
+                          int k, int kc, void *stream) {
+    const int64_t ldq = cw_score_ldq(nq);
+    int rc = cw_dense_node_scores_tc(tx, w->Q_dev, nq, w->xt_scratch, w->node_scores, ldq, stream);
+    if (rc) return rc;
+    if ((rc = cw_dense_paths_topk(ix, w->node_scores, ldq, nq, kc, nullptr, w->cand_sid, w->cand_score, w->scratch, stream)))
+        return rc;
+    return cw_dense_rescore(s, ix, tx->rows, tx->pos_of_sid, w->Q_dev, nq, kc, w->cand_sid, w->cand_score, k, tx->hmax, tx->lmax,
+                            tx->wfac, tx->eps_scale, w->out_sid_dev, w->out_score_dev, w->fail, stream);
+}
+
+// flagged list of the last tensor_predict -> host, ascending; returns the count (or a negative error)
+static int fetch_flagged(const cw_dense_work *w, int32_t **list, cudaStream_t st) {
+    int32_t n = 0;
+    int rc = cw_check_cuda(cudaMemcpyAsync(&n, w->fail, sizeof(int32_t), cudaMemcpyDeviceToHost, st), "flagged count");
+    if (!rc) rc = cw_check_cuda(cudaStreamSynchronize(st), "flagged count sync");
+    if (rc) return rc;
+    *list = nullptr;
+    if (n <= 0) return 0;
+    int32_t *l = new int32_t[n];
+    rc = cw_check_cuda(cudaMemcpy(l, w->fail + 1, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost), "flagged list");
+    if (rc) { delete[] l; return rc; }
+    for (int i = 1; i < n; i++) {  // insertion sort: the kernel appends in nearly ascending order
+        const int32_t v = l[i];
+        int j = i - 1;
+        for (; j >= 0 && l[j] > v; j--) l[j + 1] = l[j];
+        l[j + 1] = v;
+    }
+    *list = l;
+    return n;
+}
+
 extern "C" int cw_predict_dense_host(const cw_index *ix, const cw_tc_index *tx, const cw_store *s, const float *Q_host,
                                      int64_t nq, int k, const cw_dense_work *w, int32_t *out_sid_host,
-                                     float *out_score_host, int32_t *n_fallback, void *stream) {
+                                     float *out_score_host, int32_t *stats, void *stream) {
     if (!ix || !Q_host || !w || !w->Q_dev || !out_sid_host || !out_score_host || k < 1 ||
         (tx && (!s || !w->cand_sid || !w->cand_score || !w->fail || w->kc <= k))) {
         cw_set_error("cw_predict_dense_host: bad argument");
         return CW_E_ARG;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    if (n_fallback) *n_fallback = 0;
-    const size_t row_i = (size_t)k * sizeof(int32_t), row_f = (size_t)k * sizeof(float);
-    int rc = cw_check_cuda(cudaMemcpyAsync(w->Q_dev, Q_host, (size_t)nq * ix->D * sizeof(float), cudaMemcpyHostToDevice, st),
+    if (stats) stats[0] = stats[1] = 0;
+    const size_t row_i = (size_t)k * sizeof(int32_t), row_f = (size_t)k * sizeof(float), qrow = (size_t)ix->D * sizeof(float);
+    int rc = cw_check_cuda(cudaMemcpyAsync(w->Q_dev, Q_host, (size_t)nq * qrow, cudaMemcpyHostToDevice, st),
                            "cw_predict_dense_host: H2D");
     if (rc) return rc;
-    int32_t n_fail = 0;
-    if (tx) {  // tensor-core pre-filter + exact re-score
-        if ((rc = cw_dense_node_scores_tc(tx, w->Q_dev, nq, w->xt_scratch, w->node_scores, w->ldq, stream))) return rc;
-        if ((rc = cw_dense_paths_topk(ix, w->node_scores, w->ldq, nq, w->kc, nullptr, w->cand_sid, w->cand_score, w->scratch,
-                                      stream)))
-            return rc;
-        if ((rc = cw_dense_rescore(s, ix, tx->rows, tx->pos_of_sid, w->Q_dev, nq, w->kc, w->cand_sid, w->cand_score, k, tx->hmax,
-                                   tx->lmax, tx->wfac, tx->eps_scale, w->out_sid_dev, w->out_score_dev, w->fail, stream)))
-            return rc;
-        rc = cw_check_cuda(cudaMemcpyAsync(&n_fail, w->fail, sizeof(int32_t), cudaMemcpyDeviceToHost, st),
-                           "cw_predict_dense_host: D2H flag");
-        if (rc) return rc;
-    } else if ((rc = fp32_predict(ix, w, nq, k, stream))) {
-        return rc;
-    }
+    rc = tx ? tensor_predict(ix, tx, s, w, nq, k, w->kc, stream) : fp32_predict(ix, w, nq, k, stream);
+    if (rc) return rc;
     rc = cw_check_cuda(cudaMemcpyAsync(out_sid_host, w->out_sid_dev, (size_t)nq * row_i, cudaMemcpyDeviceToHost, st),
                        "cw_predict_dense_host: D2H ids");
     if (rc) return rc;
     rc = cw_check_cuda(cudaMemcpyAsync(out_score_host, w->out_score_dev, (size_t)nq * row_f, cudaMemcpyDeviceToHost, st),
                        "cw_predict_dense_host: D2H scores");
     if (rc) return rc;
-    if ((rc = cw_check_cuda(cudaStreamSynchronize(st), "cw_predict_dense_host: sync"))) return rc;
-    if (n_fail == 0) return 0;
+    if (!tx) return cw_check_cuda(cudaStreamSynchronize(st), "cw_predict_dense_host: sync");
 
-    // flagged queries: answered on the FP32 pipe.  Few: their rows are compacted to the front of Q_dev (ascending,
-    // so no row is overwritten before it is moved) and scattered back; many: the whole batch is redone.
-    if (n_fallback) *n_fallback = n_fail;
-    if ((int64_t)n_fail * 4 > nq) {
-        rc = cw_check_cuda(cudaMemcpyAsync(w->Q_dev, Q_host, (size_t)nq * ix->D * sizeof(float), cudaMemcpyHostToDevice, st),
-                           "cw_predict_dense_host: H2D");
-        if (rc || (rc = fp32_predict(ix, w, nq, k, stream))) return rc;
-        cudaMemcpyAsync(out_sid_host, w->out_sid_dev, (size_t)nq * row_i, cudaMemcpyDeviceToHost, st);
-        cudaMemcpyAsync(out_score_host, w->out_score_dev, (size_t)nq * row_f, cudaMemcpyDeviceToHost, st);
-        return cw_check_cuda(cudaStreamSynchronize(st), "cw_predict_dense_host: fallback sync");
+    // Flagged queries (rare): their rows are compacted to the front of Q_dev (ascending, so no row is overwritten
+    // before it is moved), answered again -- first with kc2 candidates, what is still flagged on the FP32 pipe --
+    // and the rows scattered back to their places in the host result.
+    int32_t *list = nullptr;
+    int n_fail = fetch_flagged(w, &list, st);  // synchronises: the first-pass results are on the host
+    if (n_fail <= 0) return n_fail;
+    auto compact = [&](const int32_t *src_rows, int n) {
+        for (int i = 0; i < n; i++)
+            if (src_rows[i] != i)
+                cudaMemcpyAsync(w->Q_dev + (size_t)i * ix->D, w->Q_dev + (size_t)src_rows[i] * ix->D, qrow, cudaMemcpyDeviceToDevice, st);
+    };
+    auto scatter = [&](int dev_row, int host_row) {
+        cudaMemcpyAsync(out_sid_host + (size_t)host_row * k, w->out_sid_dev + (size_t)dev_row * k, row_i, cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(out_score_host + (size_t)host_row * k, w->out_score_dev + (size_t)dev_row * k, row_f, cudaMemcpyDeviceToHost, st);
+    };
+    compact(list, n_fail);
+    if (w->kc2 > w->kc) {
+        if (stats) stats[0] = n_fail;
+        rc = tensor_predict(ix, tx, s, w, n_fail, k, w->kc2, stream);
+        int32_t *list2 = nullptr;
+        const int n2 = rc ? rc : fetch_flagged(w, &list2, st);
+        if (n2 < 0) { delete[] list; return n2; }
+        for (int i = 0, j = 0; i < n_fail; i++) {  // rows decided at this level go home
+            if (j < n2 && list2[j] == i) { j++; continue; }
+            scatter(i, list[i]);
+        }
+        if ((rc = cw_check_cuda(cudaStreamSynchronize(st), "cw_predict_dense_host: escalation sync"))) n_fail = 0;
+        if (n2 > 0 && !rc) {
+            compact(list2, n2);
+            for (int j = 0; j < n2; j++) list[j] = list[list2[j]];
+        }
+        delete[] list2;
+        if (rc) { delete[] list; return rc; }
+        n_fail = n2;
     }
-    int32_t *list = new int32_t[n_fail];
-    rc = cw_check_cuda(cudaMemcpy(list, w->fail + 1, (size_t)n_fail * sizeof(int32_t), cudaMemcpyDeviceToHost),
-                       "cw_predict_dense_host: D2H flagged list");
-    if (!rc) {
-        for (int i = 1; i < n_fail; i++) {  // insertion sort, n_fail is small
-            const int32_t v = list[i];
-            int j = i - 1;
-            for (; j >= 0 && list[j] > v; j--) list[j + 1] = list[j];
-            list[j + 1] = v;
-        }
-        const size_t qrow = (size_t)ix->D * sizeof(float);
-        for (int i = 0; i < n_fail; i++)
-            if (list[i] != i)
-                cudaMemcpyAsync(w->Q_dev + (size_t)i * ix->D, w->Q_dev + (size_t)list[i] * ix->D, qrow, cudaMemcpyDeviceToDevice, st);
+    if (n_fail > 0) {
+        if (stats) stats[1] = n_fail;
         rc = fp32_predict(ix, w, n_fail, k, stream);
-        for (int i = 0; i < n_fail && !rc; i++) {
-            cudaMemcpyAsync(out_sid_host + (size_t)list[i] * k, w->out_sid_dev + (size_t)i * k, row_i, cudaMemcpyDeviceToHost, st);
-            cudaMemcpyAsync(out_score_host + (size_t)list[i] * k, w->out_score_dev + (size_t)i * k, row_f, cudaMemcpyDeviceToHost, st);
-        }
+        for (int i = 0; i < n_fail && !rc; i++) scatter(i, list[i]);
         if (!rc) rc = cw_check_cuda(cudaStreamSynchronize(st), "cw_predict_dense_host: fallback sync");
     }
     delete[] list;

@@ -12,8 +12,9 @@
 // exactly), so only the m candidates at or above that threshold are re-scored; if all kc candidates
 // are (m == kc) the list may be incomplete and the query is flagged for the FP32 path instead.
 // Result: ids and scores bit-identical to the "fp32" mode (tests/test_gpu_parity.py asserts equality).
-// eps is a statistical bound, several times the largest deviation seen over 1e9 node scores, not a
-// worst-case proof (a worst-case fp32 accumulation bound would be useless for either kernel).
+// eps is a statistical bound -- operand term 2^-18 T plus (4 + 3 sqrt(max_len)) ulps of the score magnitude for the
+// roundings of the two FMA chains -- 4.7x the largest deviation seen over 1.3e9 leaf scores at cfg3 (depth 14) and
+// 5e8 at cfg4 (depth 66), not a worst-case proof (a worst-case fp32 accumulation bound is useless for either kernel).
 //
 // Strict arithmetic (-fmad=false; FMAs are explicit): r / mb come from a row-major copy of the
 // index operands built here with the same operations cw_index.cu uses for the index tiles.
@@ -82,7 +83,7 @@ rescore_kernel(const RescoreArgs a) {
         float x2 = 0.0f;
         for (int w = 0; w < RS_WARPS; w++) x2 += red[w];
         const float tq = 2.0f * (x2 * a.inv_prior + a.hmax);
-        const float eps = a.wfac * (a.eps_scale * tq + a.mag_scale * (float)(4 + ML) * 0.5f * (a.lmax + a.hmax + tq));
+        const float eps = a.wfac * (a.eps_scale * tq + a.mag_scale * (4.0f + 3.0f * sqrtf((float)ML)) * 0.5f * (a.lmax + a.hmax + tq));
         const float *cs = a.cand_score + q * kc;
         const int *ci = a.cand_sid + q * kc;
         int nvalid = 0, m = 0;

@@ -15,6 +15,7 @@ random.shuffle -- exact ties are broken by ascending sentence id.
 """
 import ctypes as C
 import json
+import os
 
 import numpy as np
 import torch
@@ -26,7 +27,7 @@ from .tree import CobwebNode, CobwebTorchTree
 class DenseIndex:
     """Device-resident prediction index (build_prediction_index, CobwebWrapper.py:91-208)."""
 
-    SCORE_BUDGET_BYTES = 8 << 30  # node-score scratch per query chunk
+    SCORE_BUDGET_BYTES = 16 << 30  # node-score scratch per query chunk
     # where the node scores are computed: "fp32" = FP32 pipe, (x*r + mb)^2 per triple (cw_dense.cu);
     # "tf32x3" = tcgen05 contraction with hi/lo-split TF32 operands (cw_tensor.cu, ~1e-6 relative to "fp32") as a
     # pre-filter for top-kc candidates, followed by the exact re-score (cw_rescore.cu): top-k ids and scores are
@@ -139,7 +140,7 @@ class DenseIndex:
         return b
 
     def chunk_queries(self):
-        return int(max(128, min(65535, self.SCORE_BUDGET_BYTES // (self.ld * 4)) // 128 * 128))
+        return int(max(256, min(65535, self.SCORE_BUDGET_BYTES // (self.ld * 4)) // 256 * 256))  # whole 256-query tiles
 
     def workspace(self, nq, k):
         """Device work buffers for chunks of up to nq queries and top-k up to k (grown on demand)."""
@@ -161,7 +162,7 @@ class DenseIndex:
             sid=torch.empty((nq, k), dtype=torch.int32, device=dev),
             val=torch.empty((nq, k), dtype=torch.float32, device=dev),
         )
-        kc = max(k, self.candidates(k))
+        kc = max(k, self.candidates(k), self.candidates(k, 1))
         ws["scratch"] = torch.empty(max(1, nq * L.cw_topk_chunks(max(self.n_pos, 1)) * kc * 2), dtype=torch.int32, device=dev)
         ws["cand_sid"] = torch.empty((nq, kc), dtype=torch.int32, device=dev)
         ws["cand_val"] = torch.empty((nq, kc), dtype=torch.float32, device=dev)
@@ -169,14 +170,19 @@ class DenseIndex:
         self._ws = ws
         return ws
 
-    def candidates(self, k):
-        """Candidates per query the tensor-core pre-filter hands to the exact re-score (0 = this k is served by
-        the FP32 path: k too large, or paths too long for the re-score kernel's shared memory)."""
-        if k < 1 or k > 32 or not self.n_pos:
+    def candidates(self, k, level=0):
+        """Candidates per query the tensor-core pre-filter hands to the exact re-score: level 0 = first attempt,
+        level 1 = second attempt for the queries the first one flagged (0 = no such level: this k is served by the
+        FP32 path -- k too large, or paths too long for the re-score kernel's shared memory)."""
+        if k < 1 or k > 32 or not self.n_pos or level > 1:
             return 0
         # enough that the weakest candidate sits below (k-th best) - 2 eps: at cfg3 the gap between ranks 10 and 24
         # is >= 3x that margin for every query (tools/tc_gap_probe.py); k-lists of up to 32 use the fast insertion path
         kc = 24 if k <= 10 else (32 if k <= 16 else 2 * k)
+        if level == 1:
+            if kc >= _lib.RESCORE_MAX_KC:
+                return 0
+            kc = _lib.RESCORE_MAX_KC
         if kc * self.max_len > 65535 or _lib.load().cw_rescore_smem_bytes(self.tree.d, self.max_len, kc) > 200 * 1024:
             return 0
         return kc
@@ -186,7 +192,7 @@ class DenseIndex:
         w.Q_dev, w.xt_scratch, w.node_scores, w.ldq = ws["q"].data_ptr(), ws["xt"].data_ptr(), ws["scores"].data_ptr(), ws["ldq"]
         w.out_sid_dev, w.out_score_dev, w.scratch = ws["sid"].data_ptr(), ws["val"].data_ptr(), ws["scratch"].data_ptr()
         w.cand_sid, w.cand_score, w.fail = ws["cand_sid"].data_ptr(), ws["cand_val"].data_ptr(), ws["fail"].data_ptr()
-        w.kc = self.candidates(k)
+        w.kc, w.kc2 = self.candidates(k), self.candidates(k, 1)
         return w
 
     def node_scores(self, Q):
@@ -196,11 +202,12 @@ class DenseIndex:
         self._node_scores_call(Q, nq, ws)
         return ws["scores"][: self.nn, :nq].T
 
-    def predict(self, Q, k, want_leaf_scores=False, mode=None):
+    def predict(self, Q, k, want_leaf_scores=False, mode=None, _level=0):
         """Device batch -> (sids [nq,k] int32, scores [nq,k], leaf_scores [nq,L] or None).  mode overrides
-        self.mode for this call.  In "tf32x3" mode top-k goes pre-filter -> exact re-score -> FP32 answer for
-        flagged queries (self.n_fallback counts them); leaf_scores, if requested, come from the same node scores
-        as the top-k of that mode (approximate for "tf32x3")."""
+        self.mode for this call.  In "tf32x3" mode top-k goes pre-filter -> exact re-score; flagged queries are
+        answered again with more candidates (self.n_escalated) and what is still flagged on the FP32 pipe
+        (self.n_fallback); leaf_scores, if requested, come from the same node scores as the top-k of that mode
+        (approximate for "tf32x3")."""
         L = _lib.load()
         if want_leaf_scores and self.sentence_ids is not None:
             raise ValueError("leaf scores are indexed by global sentence id; not available on a sentence shard")
@@ -212,7 +219,7 @@ class DenseIndex:
                 return self.predict(Q, k, want_leaf_scores)
             finally:
                 self.mode = prev
-        kc = self.candidates(k) if (mode == "tf32x3" and not want_leaf_scores) else 0
+        kc = self.candidates(k, _level) if (mode == "tf32x3" and not want_leaf_scores) else 0
         if mode == "tf32x3" and kc == 0 and k > 0 and not want_leaf_scores:
             return self.predict(Q, k, mode="fp32")  # this k / depth is not served by the re-score kernel
         nq_total = Q.shape[0]
@@ -245,12 +252,17 @@ class DenseIndex:
                                                  ws["scratch"].data_ptr(), _lib.stream_ptr()), "cw_dense_paths_topk")
         if redo:
             idx = torch.cat(redo)
-            self.n_fallback += int(idx.numel())
-            s2, v2, _ = self.predict(Q[idx].contiguous(), k, mode="fp32")
+            if self.candidates(k, _level + 1):
+                self.n_escalated += int(idx.numel())
+                s2, v2, _ = self.predict(Q[idx].contiguous(), k, _level=_level + 1)
+            else:
+                self.n_fallback += int(idx.numel())
+                s2, v2, _ = self.predict(Q[idx].contiguous(), k, mode="fp32")
             sids[idx], vals[idx] = s2, v2
         return sids, vals, leaf
 
-    n_fallback = 0  # queries answered by the FP32 path because the re-score margin did not hold
+    n_escalated = 0  # queries whose first candidate list could not be decided and were re-run with more candidates
+    n_fallback = 0   # queries answered by the FP32 path because the re-score margin did not hold at any level
 
     def predict_host(self, Q_host, k, out_sid=None, out_val=None):
         """Host batch (numpy / pinned tensor) -> host ids/scores through the single C-ABI call
@@ -263,16 +275,17 @@ class DenseIndex:
             out_sid = torch.empty((nq_total, k), dtype=torch.int32)
             out_val = torch.empty((nq_total, k), dtype=torch.float32)
         tensor = self.mode == "tf32x3" and self.candidates(k) > 0
-        nfb = C.c_int32(0)
+        nfb = (C.c_int32 * 2)(0, 0)
         for lo in range(0, nq_total, step):
             nq = min(step, nq_total - lo)
             ws = self.workspace(min(step, nq_total), k)
             w = self._work_struct(ws, k)
             _lib.check(L.cw_predict_dense_host(C.byref(self.ix), C.byref(self.tx) if tensor else None,
                                                self.tree.store.struct(), Qh[lo:lo + nq].data_ptr(), nq, k, C.byref(w),
-                                               out_sid[lo:lo + nq].data_ptr(), out_val[lo:lo + nq].data_ptr(), C.byref(nfb),
+                                               out_sid[lo:lo + nq].data_ptr(), out_val[lo:lo + nq].data_ptr(), nfb,
                                                _lib.stream_ptr()), "cw_predict_dense_host")
-            self.n_fallback += nfb.value
+            self.n_escalated += nfb[0]
+            self.n_fallback += nfb[1]
         return out_sid, out_val
 
 
@@ -382,7 +395,9 @@ class CobwebWrapper:
         self._index = DenseIndex(self.tree, self._leaf_of_sentence, self._level_weights).set_mode(self.dense_mode)
         self.max_depth = max(self.max_depth, self._index.max_depth)
 
-    dense_mode = "fp32"
+    # default scoring mode of new wrappers; "tf32x3" returns the same ids and scores faster but builds two more
+    # operand copies per index (DenseIndex.MODES)
+    dense_mode = os.environ.get("COBWEB_B200_DENSE_MODE", "fp32")
 
     def set_dense_mode(self, mode):
         """Additive: where cobweb_predict_fast / predict_fast_batch compute node scores -- "fp32" (FP32 pipe,

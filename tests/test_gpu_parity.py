@@ -505,25 +505,34 @@ def test_tensor_core_predict_fallback_paths():
     kernel's range, fewer sentences than candidates, a level-weight schedule: always the FP32 path's answer."""
     rng = np.random.default_rng(5)
     base = synth.corpus(40, 64, "unit", seed=6)
-    x = np.concatenate([np.repeat(base[:3], 50, axis=0), base[3:]]).astype(np.float32)  # 3 leaves with 50 sentences each
+    # leaves with 70, 70 and 40 identical sentences: more equal-scoring sentences than first-level (24) resp. second-level
+    # (64) candidates
+    x = np.concatenate([np.repeat(base[:2], 70, axis=0), np.repeat(base[2:3], 40, axis=0), base[3:]]).astype(np.float32)
     x = x[rng.permutation(len(x))]
     w = CobwebWrapper(corpus=[None] * len(x), corpus_embeddings=x)
     q = np.concatenate([base[:3] + 1e-3, synth.queries(x, 61, "unit", seed=7)[0]]).astype(np.float32)
     qd = torch.from_numpy(q).cuda()
-    w.set_level_weights([1.0, 0.5, 2.0, 1.0, 0.25])
-    w.build_prediction_index()
-    ix = w._index
-    for k in (1, 10, 32, 40):
-        ix.set_mode("fp32")
-        ids32, v32, _ = ix.predict(qd, k)
-        ix.set_mode("tf32x3")
-        n0 = ix.n_fallback
-        ids, vals, _ = ix.predict(qd, k)
-        assert torch.equal(ids, ids32) and torch.equal(vals, v32), k
-        if k == 10:
-            assert ix.n_fallback - n0 >= 3  # the three duplicate-heavy queries cannot be decided from 24 candidates
-        hs, hv = ix.predict_host(q, k)
-        assert np.array_equal(hs.numpy(), ids32.cpu().numpy()) and np.array_equal(hv.numpy(), v32.cpu().numpy()), k
+    for weights in (None, [1.0, 0.5, 2.0, 1.0, 0.25]):
+        if weights is not None:
+            w.set_level_weights(weights)
+        w.build_prediction_index()
+        ix = w._index
+        for k in (1, 10, 32, 40):
+            ix.set_mode("fp32")
+            ids32, v32, _ = ix.predict(qd, k)
+            ix.set_mode("tf32x3")
+            for call in ("device", "host"):
+                n0, e0 = ix.n_fallback, ix.n_escalated
+                if call == "device":
+                    ids, vals, _ = ix.predict(qd, k)
+                    assert torch.equal(ids, ids32) and torch.equal(vals, v32), (k, weights)
+                else:
+                    hs, hv = ix.predict_host(q, k)
+                    assert np.array_equal(hs.numpy(), ids32.cpu().numpy()) and np.array_equal(hv.numpy(), v32.cpu().numpy()), k
+                if k == 10 and weights is None:
+                    # with the default weights a query next to a leaf ranks that leaf first: its 70 (resp. 40) equal-scoring
+                    # sentences cannot be decided from 24 candidates, the 70 not from 64 either
+                    assert ix.n_escalated - e0 >= 3 and ix.n_fallback - n0 >= 1, (call, ix.n_escalated - e0, ix.n_fallback - n0)
     # fewer sentences than candidates
     w2 = CobwebWrapper(corpus=[None] * 12, corpus_embeddings=base[:12])
     w2.build_prediction_index()
