@@ -203,7 +203,11 @@ def _run_engine(args, wl):
         torch.cuda.synchronize()
         log(f"[bench] rank {rank}: store broadcast {time.time() - t0:.2f}s")
     w.set_dense_mode(args.mode)
+    torch.cuda.synchronize()
+    t0 = time.time()
     w.build_prediction_index()
+    torch.cuda.synchronize()
+    index_build_s = time.time() - t0
     ix = w._index
     tensor = args.mode == "tf32x3" and ix.candidates(k) > 0
     # this rank's batch: global batch = world * qn, contiguous shards
@@ -433,6 +437,8 @@ def _run_engine(args, wl):
         "clocks": clocks,
         "recall_at_k": recall,
         "fp32_path": fp32,
+        "index_build_s": index_build_s,
+        "index_bytes": ix.bytes(),
         "ffma_peak_tflops": ffma,
         "escalated_queries": n_escalated, "fallback_queries": n_fallback,
         "queries_answered": int(qn * (2 * max(args.warmup, 3) + 2 * args.steps)),
