@@ -237,6 +237,13 @@ __device__ __forceinline__ bool cand_better(float as, int ai, float bs, int bi) 
     return ai < bi;
 }
 
+// order-preserving float <-> int key (for atomicMax on scores)
+__device__ __forceinline__ int float_key(float f) {
+    const int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float key_float(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff); }
+
 // Rare path of the kernel below (the path length changes a handful of times per chunk); kept out
 // of line so that its binary64 division does not inflate the hot loop's register allocation.
 __device__ __noinline__ void fill_weight_row(float *wl, const double *lw, int len, int lane) {
@@ -280,7 +287,7 @@ __global__ void __launch_bounds__(256, 3)
 paths_topk_kernel(const float *__restrict__ ST, unsigned ldq, long long nq, int n_pos, int max_len,
                   const int *__restrict__ path_pm, const int4 *__restrict__ pos_rec,
                   const double *__restrict__ level_w, int k, float *leaf_scores, float *cand_s, int *cand_i,
-                  int n_chunks, int chunk_len) {
+                  int n_chunks, int chunk_len, int *shared_thr) {
     extern __shared__ __align__(16) unsigned char pt_smem[];
     // level weights in binary64; the path weight of level j on a path of length len is
     // (float)(level_w[j] / len), the fp32 value the reference stores in its sparse path matrix
@@ -311,6 +318,13 @@ paths_topk_kernel(const float *__restrict__ ST, unsigned ldq, long long nq, int 
     float thr_s = NEG_INF;
     int thr_i = 0x7fffffff;
     const bool collect = k > 0 && qvalid;
+    // Threshold shared by the chunks of a query: the k-th best of ANY chunk's full list is a lower bound of the k-th
+    // best over all positions, so a score strictly below it cannot be in the final top-k.  Each lane publishes its own
+    // k-th best (atomicMax on an order-preserving integer key) and re-reads the shared bound once per 32 positions;
+    // without it every chunk pays the k ln(n/k) warm-up insertions of a cold list.  The merged result is the exact
+    // top-k whatever the timing.
+    float gthr = NEG_INF, published = NEG_INF;
+    int *gslot = shared_thr + (qvalid ? q : 0);
     int wl_len = -1;  // path length the per-warp weight row wl[] was computed for
 
     // record of position p0 + r (lane-parallel): the first position of a chunk recomputes its whole path
@@ -356,6 +370,13 @@ paths_topk_kernel(const float *__restrict__ ST, unsigned ldq, long long nq, int 
           __syncwarp();
       }
       nb = load_rec(rb + 64 + lane);
+      if (collect) {
+          if (thr_i != 0x7fffffff && thr_s > published) {  // list full and its k-th best moved: publish
+              published = thr_s;
+              atomicMax(gslot, float_key(thr_s));
+          }
+          gthr = fmaxf(gthr, key_float(__ldcg(gslot)));
+      }
       const int re = min(n, rb + 32);
       for (int r = rb; r < re; r++) {
         prefetch(r + PF_DIST);
@@ -400,7 +421,8 @@ paths_topk_kernel(const float *__restrict__ ST, unsigned ldq, long long nq, int 
         if (LEAF && qvalid) leaf_scores[q * n_pos + sid] = acc;
         // top-k: lanes whose candidate beats their query's k-th best are served one at a time by
         // the whole warp (lane r handles rank r of that query's list): no divergent shifting loops
-        unsigned need = __ballot_sync(0xffffffffu, collect && (acc > thr_s || (acc == thr_s && (unsigned)sid < (unsigned)thr_i)));
+        unsigned need = __ballot_sync(0xffffffffu, collect && acc >= gthr &&
+                                                       (acc > thr_s || (acc == thr_s && (unsigned)sid < (unsigned)thr_i)));
         if (K32) {
             // one rank per lane: read, ballot the insertion point, shift by one, done
             while (need) {
@@ -591,7 +613,8 @@ extern "C" int cw_dense_node_scores(const cw_index *ix, const float *Q, int64_t 
 
 // Upper bound of position chunks per query (sizes the caller's candidate scratch); the launch
 // picks fewer, larger chunks when the batch alone fills the GPU.
-extern "C" int64_t cw_topk_chunks(int64_t n_pos) { return (n_pos + 1023) / 1024; }
+// one extra chunk worth of scratch holds the per-query thresholds shared between the chunks
+extern "C" int64_t cw_topk_chunks(int64_t n_pos) { return (n_pos + 1023) / 1024 + 1; }
 
 extern "C" int cw_dense_paths_topk(const cw_index *ix, const float *node_scores, int64_t ldq, int64_t nq, int k,
                                    float *leaf_scores, int32_t *out_sid, float *out_score, int32_t *scratch,
@@ -632,13 +655,19 @@ extern "C" int cw_dense_paths_topk(const cw_index *ix, const float *node_scores,
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     long long want = (long long)sms * (best_warps / wpb) / gblocks;
-    const long long max_chunks = cw_topk_chunks(ix->n_pos);
+    const long long max_chunks = cw_topk_chunks(ix->n_pos) - 1;
     if (want > max_chunks) want = max_chunks;
     if (want < 1) want = 1;
     const int chunk_len = (int)((ix->n_pos + want - 1) / want);
     const int n_chunks = (ix->n_pos + chunk_len - 1) / chunk_len;
     float *cand_s = reinterpret_cast<float *>(scratch);
     int *cand_i = scratch + (size_t)nq * n_chunks * (k > 0 ? k : 1);
+    int *shared_thr = scratch + (size_t)2 * nq * n_chunks * (k > 0 ? k : 1);  // [nq] inside the extra chunk of scratch
+    if (k > 0) {
+        // 0x80808080 is the key of a large negative score: below every real one
+        int rc = cw_check_cuda(cudaMemsetAsync(shared_thr, 0x80, (size_t)nq * sizeof(int), st), "cw_dense_paths_topk: memset");
+        if (rc) return rc;
+    }
     const size_t smem = fixed + (size_t)wpb * per_warp;
     auto kern = leaf_scores ? (k <= 32 ? paths_topk_kernel<true, true> : paths_topk_kernel<true, false>)
                             : (k <= 32 ? paths_topk_kernel<false, true> : paths_topk_kernel<false, false>);
@@ -649,7 +678,7 @@ extern "C" int cw_dense_paths_topk(const cw_index *ix, const float *node_scores,
     }
     kern<<<dim3(n_chunks, (unsigned)gblocks), wpb * 32, smem, st>>>(
         node_scores, (unsigned)ldq, nq, ix->n_pos, ix->max_len, ix->path_idx, reinterpret_cast<const int4 *>(ix->pos_rec),
-        ix->level_w, k, leaf_scores, cand_s, cand_i, n_chunks, chunk_len);
+        ix->level_w, k, leaf_scores, cand_s, cand_i, n_chunks, chunk_len, shared_thr);
     if (k > 0)
         merge_topk_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, st>>>(cand_s, cand_i, nq, n_chunks, k, out_sid, out_score);
     return cw_check_cuda(cudaGetLastError(), "cw_dense_paths_topk");

@@ -289,8 +289,17 @@ def test_properties_at_scale():
     assert (b["nsent"][kids] == 0).all() and b["nsent"].sum() == n  # sentences live on leaves only
     assert (t["child_cnt"][w._leaf_of_sentence] == 0).all()
     q = x[:512]
-    ids, _ = w.predict_fast_batch(q, 10)
+    ids, vals = w.predict_fast_batch(q, 10)
     assert np.mean([i in g for i, g in enumerate(ids.cpu().numpy())]) > 0.99  # a document retrieves itself
+    # the tensor-core path at this size (several node tiles per SM, whitened operands = the cancellation-heavy case):
+    # same ids, same scores, on a batch that is not a multiple of any tile
+    w.set_dense_mode("tf32x3")
+    qb, _ = synth.queries(x, 3001, "whitened", seed=2)
+    ids_t, vals_t = w.predict_fast_batch(np.concatenate([q, qb]), 10)
+    w.set_dense_mode("fp32")
+    ids_f, vals_f = w.predict_fast_batch(np.concatenate([q, qb]), 10)
+    assert torch.equal(ids_t, ids_f) and torch.equal(vals_t, vals_f)
+    assert torch.equal(ids_t[:512], ids) and w._index.n_fallback <= 8
     # oracle cross-check on the engine-built tree: load it into the oracle, compare best-first on a sample
     mean, m2 = w.tree.store.rows(b["order"])
     ref = OracleTree(d)
