@@ -162,7 +162,8 @@ class DenseIndex:
             sid=torch.empty((nq, k), dtype=torch.int32, device=dev),
             val=torch.empty((nq, k), dtype=torch.float32, device=dev),
         )
-        kc = max(k, self.candidates(k), self.candidates(k, 1))
+        c0 = self.candidates(k)
+        kc = max(k, c0, 32 if c0 else 0, self.candidates(k, 1))  # 32: room for the adaptive first level
         ws["scratch"] = torch.empty(max(1, nq * L.cw_topk_chunks(max(self.n_pos, 1)) * kc * 2), dtype=torch.int32, device=dev)
         ws["cand_sid"] = torch.empty((nq, kc), dtype=torch.int32, device=dev)
         ws["cand_val"] = torch.empty((nq, kc), dtype=torch.float32, device=dev)
@@ -176,9 +177,12 @@ class DenseIndex:
         FP32 path -- k too large, or paths too long for the re-score kernel's shared memory)."""
         if k < 1 or k > 32 or not self.n_pos or level > 1:
             return 0
-        # enough that the weakest candidate sits below (k-th best) - 2 eps: at cfg3 the gap between ranks 10 and 24
-        # is >= 3x that margin for every query (tools/tc_gap_probe.py); k-lists of up to 32 use the fast insertion path
-        kc = 24 if k <= 10 else (32 if k <= 16 else 2 * k)
+        # enough that the weakest candidate sits below (k-th best) - 2 eps for (nearly) every query: the first level
+        # starts at 24 (k <= 10: at cfg3 and cfg4 the gap between ranks 10 and 24 exceeds the margin for all but
+        # ~1 query in 10^4, tools/tc_gap_probe.py; 16 would save 0.9 ms of path kernel per 10k queries but the
+        # second pass for its 0.1 % flagged queries costs more) and is raised by _adapt() when more than 0.5 % of
+        # a batch had to be escalated; lists up to 32 use the fast insertion path
+        kc = min(max(self._kc0, k + 6), 32) if k <= 16 else 2 * k
         if level == 1:
             if kc >= _lib.RESCORE_MAX_KC:
                 return 0
@@ -250,6 +254,8 @@ class DenseIndex:
                                                  leaf[lo:lo + nq].data_ptr() if leaf is not None else None,
                                                  sids[lo:lo + nq].data_ptr(), vals[lo:lo + nq].data_ptr(),
                                                  ws["scratch"].data_ptr(), _lib.stream_ptr()), "cw_dense_paths_topk")
+        if kc and _level == 0:
+            self._adapt(nq_total, sum(int(r.numel()) for r in redo))
         if redo:
             idx = torch.cat(redo)
             if self.candidates(k, _level + 1):
@@ -260,6 +266,12 @@ class DenseIndex:
                 s2, v2, _ = self.predict(Q[idx].contiguous(), k, mode="fp32")
             sids[idx], vals[idx] = s2, v2
         return sids, vals, leaf
+
+    _kc0 = 24        # first-level candidates per query (k <= 16), adapted to the escalation rate
+
+    def _adapt(self, n_queries, n_flagged):
+        if n_queries >= 64 and n_flagged > 0.005 * n_queries and self._kc0 < 32:
+            self._kc0 += 8
 
     n_escalated = 0  # queries whose first candidate list could not be decided and were re-run with more candidates
     n_fallback = 0   # queries answered by the FP32 path because the re-score margin did not hold at any level
@@ -286,6 +298,8 @@ class DenseIndex:
                                                _lib.stream_ptr()), "cw_predict_dense_host")
             self.n_escalated += nfb[0]
             self.n_fallback += nfb[1]
+            if tensor:
+                self._adapt(nq, nfb[0])
         return out_sid, out_val
 
 

@@ -497,7 +497,7 @@ def test_tensor_core_predict_matches_fp32_path(n, d, kind, k):
     ref.build_index()
     rns, _ = ref.dense_scores(q[:64])
     np.testing.assert_allclose(nstc[:64].cpu().numpy(), rns, rtol=1e-5, atol=floor + 8 * EPS32 * float(np.abs(rns).max()))
-    assert ix.candidates(k) in (24, 32, 64)
+    assert k < ix.candidates(k) <= 64
     before = ix.n_fallback
     ids, vals, _ = ix.predict(qd, k)
     assert torch.equal(ids, ids32) and torch.equal(vals, v32)
