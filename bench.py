@@ -329,6 +329,21 @@ def _run_engine(args, wl):
     bf = w.tree.categorize_batch(q_dev[:nbf], retrieve_k=k, max_nodes=w.max_init_search)
     bf_rows = float(bf["lp_calls"].float().mean().item())
 
+    # the reference's own usage pattern: one query per call through the reference-shaped API (its published tables
+    # quote ms per query for cobweb_predict_fast), host vector in, python list of ids out
+    def single_query_ms(n=30):
+        w.cobweb_predict_fast(q_all[0], k=k, return_ids=True, is_embedding=True)
+        torch.cuda.synchronize()
+        t0 = time.time()
+        for i in range(n):
+            w.cobweb_predict_fast(q_all[i % qn], k=k, return_ids=True, is_embedding=True)
+        return (time.time() - t0) / n * 1e3
+    single = {args.mode: single_query_ms()}
+    if tensor:
+        w.set_dense_mode("fp32")
+        single["fp32"] = single_query_ms()
+        w.set_dense_mode("tf32x3")
+
     # correctness inside the bench: recall@k of the timed configuration (target among returned ids)
     ids, _ = step_device()
     got = ids.cpu().numpy()[lo:hi] if (world > 1 and not store_mode) else ids.cpu().numpy()
@@ -437,6 +452,7 @@ def _run_engine(args, wl):
         "clocks": clocks,
         "recall_at_k": recall,
         "fp32_path": fp32,
+        "single_query_ms": single,
         "index_build_s": index_build_s,
         "index_bytes": ix.bytes(),
         "ffma_peak_tflops": ffma,

@@ -147,7 +147,9 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name)
     assert lib.cw_version() == 100
     assert ctypes.sizeof(_lib.CwStore) == 24 + 12 * 8
-    assert lib.cw_topk_chunks(1025) == 2 and lib.cw_xt_floats(129, 20) == 2 * 2 * 16 * 128
+    assert lib.cw_topk_chunks(1025) == 3 and lib.cw_xt_floats(129, 20) == 2 * 2 * 16 * 128  # 2 chunks + the threshold slot
+    assert lib.cw_tc_a_bytes(257, 20) == 2 * 3 * 2 * 256 * 64 and lib.cw_tc_b_bytes(300, 9) == 2 * 2 * 2 * 256 * 64
+    assert ctypes.sizeof(_lib.CwTcIndex) == 16 + 4 * 8 + 16 and ctypes.sizeof(_lib.CwDenseWork) == 10 * 8 + 8
 
 
 def test_engine_refuses_to_run_without_cuda():
