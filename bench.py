@@ -338,11 +338,13 @@ def _run_engine(args, wl):
         for i in range(n):
             w.cobweb_predict_fast(q_all[i % qn], k=k, return_ids=True, is_embedding=True)
         return (time.time() - t0) / n * 1e3
-    single = {args.mode: single_query_ms()}
-    if tensor:
-        w.set_dense_mode("fp32")
-        single["fp32"] = single_query_ms()
-        w.set_dense_mode("tf32x3")
+    single = None
+    if not store_mode:
+        single = {args.mode: single_query_ms()}
+        if tensor:
+            w.set_dense_mode("fp32")
+            single["fp32"] = single_query_ms()
+            w.set_dense_mode("tf32x3")
 
     # correctness inside the bench: recall@k of the timed configuration (target among returned ids)
     ids, _ = step_device()
