@@ -135,26 +135,39 @@ rescore_kernel(const RescoreArgs a) {
             if (f != c) slot[e] = slot[f * ML + j];
         }
         const int U = *ucount;
-        // ---- exact node scores: lane = unique row, the warp stages 32 attributes of its 32 rows at a time
+        // ---- exact node scores: the unique rows are dealt evenly to the warps, lane = row.  Per 32 attributes the
+        // warp reads its rows with coalesced 256-byte loads (all in flight at once, and one segment ahead of the
+        // arithmetic), transposes them through shared memory, and every lane runs its row's FMA chain in order.
         float2 *stw = stage + warp * 32 * 33;
-        for (int g = warp; g * 32 < U; g += RS_WARPS) {
-            const int u = g * 32 + lane;
-            const int b = u < U ? ulist[u] : -1;
+        for (int base0 = 0; base0 < U; base0 += 32 * RS_WARPS) {
+            const int in_round = min(U - base0, 32 * RS_WARPS);
+            const int per = (in_round + RS_WARPS - 1) / RS_WARPS;
+            const int my_lo = base0 + warp * per;
+            const int my_n = max(0, min(per, base0 + in_round - my_lo));
+            if (my_n == 0) continue;  // warp-uniform
+            const int u = my_lo + lane;
+            const int b = lane < my_n ? ulist[u] : -1;
             float acc = 0.0f;
-            for (int d0 = 0; d0 < D; d0 += 32) {
+            float2 o[32];
+            auto fetch = [&](int d0) {
                 const int d = d0 + lane;
-#pragma unroll 8
+#pragma unroll
                 for (int r = 0; r < 32; r++) {
                     const int rb = __shfl_sync(0xffffffffu, b, r);
-                    float2 o = make_float2(0.0f, 0.0f);
-                    if (rb >= 0 && d < D) o = a.RM[(size_t)rb * D + d];
-                    stw[r * 33 + lane] = o;
+                    o[r] = make_float2(0.0f, 0.0f);
+                    if (rb >= 0 && d < D) o[r] = a.RM[(size_t)rb * D + d];
                 }
+            };
+            fetch(0);
+            for (int d0 = 0; d0 < D; d0 += 32) {
+#pragma unroll
+                for (int r = 0; r < 32; r++) stw[r * 33 + lane] = o[r];
                 __syncwarp();
+                if (d0 + 32 < D) fetch(d0 + 32);
                 const int nd = min(32, D - d0);
                 for (int j = 0; j < nd; j++) {
-                    const float2 o = stw[lane * 33 + j];
-                    const float t = __fmaf_rn(xq[d0 + j], o.x, o.y);
+                    const float2 v = stw[lane * 33 + j];
+                    const float t = __fmaf_rn(xq[d0 + j], v.x, v.y);
                     acc = __fmaf_rn(t, t, acc);
                 }
                 __syncwarp();
