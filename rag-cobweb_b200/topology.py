@@ -128,3 +128,81 @@ def generate_weight_schedule(schedule_type, max_depth, **kwargs):
         base = kwargs.get("base", 0.5)
         return [base ** i for i in range(max_depth)]
     raise ValueError(f"Unknown schedule type: {schedule_type}")
+
+
+def fused_layout(order, parent_b, depth, leaf_of_sentence, level_weights=None, n_slots=None, sentence_ids=None,
+                 tile=256, sample_every=8):
+    """Layout of the fused tensor-core predict (DenseIndex mode "tf32x3f").
+
+    The leaf score sum_j (w_j/len) s_j is rewritten as (C[parent] + w_leaf * s_leaf) / len with the cumulative
+    ancestor sums C[n] = C[parent(n)] + w_depth(n) * s_n, which do not depend on the leaf.  Index rows are split
+    into internal rows (BFS order, levels contiguous) and sentence-leaf rows; the leaf rows are cut into tiles of
+    `tile` rows and every `sample_every`-th full tile is moved to the front: those tiles are scored first and give
+    every query a lower bound of its k-th best score, against which the remaining tiles are filtered in the scoring
+    kernel's epilogue.  Returns a dict of numpy arrays (rows are BFS index rows of `order`):
+      int_rows, int_parent (internal index or -1), int_w (float32), level_off (internal rows per depth, prefix sums),
+      leaf_rows (new leaf order), leaf_parent (internal index or -1), leaf_w, leaf_inv_len (float32), n_sample_tiles,
+      sent_off [n_leaf + 1], sent_ids (sentence ids, ascending per leaf),
+      flat_pos_rec [n_pos_s, 4], flat_path [n_pos_s, 1] (flat index over the sentences of the sampled leaves)."""
+    order = np.asarray(order, np.int64)
+    nn = len(order)
+    n_slots = int(order.max()) + 1 if n_slots is None else n_slots
+    row_of = np.full(n_slots, -1, np.int64)
+    row_of[order] = np.arange(nn)
+    leaf_of_sentence = np.asarray(leaf_of_sentence, np.int64)
+    sids = np.arange(len(leaf_of_sentence), dtype=np.int64) if sentence_ids is None else np.asarray(sentence_ids, np.int64)
+    leaf_row_of_sent = row_of[leaf_of_sentence]
+    if (leaf_row_of_sent < 0).any():
+        raise ValueError("a sentence points at a node that is not in the index")
+    is_leaf = np.zeros(nn, bool)
+    is_leaf[leaf_row_of_sent] = True
+    if is_leaf[np.maximum(parent_b, 0)][parent_b >= 0].any():
+        raise ValueError("a node holding sentences has children")
+    max_len = int(depth[is_leaf].max()) + 1
+    lw = [1.0] * 6 if level_weights is None else list(level_weights)
+    wrow = np.ones(max_len, np.float64)
+    wrow[: min(len(lw), max_len)] = lw[:max_len]
+    # internal rows: BFS order, so parents come first and every depth is one contiguous range
+    int_rows = np.nonzero(~is_leaf)[0]
+    int_of_row = np.full(nn, -1, np.int64)
+    int_of_row[int_rows] = np.arange(len(int_rows))
+    int_parent = np.where(parent_b[int_rows] >= 0, int_of_row[np.maximum(parent_b[int_rows], 0)], -1)
+    int_depth = depth[int_rows]
+    int_w = wrow[np.minimum(int_depth, max_len - 1)].astype(np.float32)
+    n_levels = int(int_depth.max()) + 1 if len(int_rows) else 0
+    level_off = np.concatenate([[0], np.cumsum(np.bincount(int_depth, minlength=n_levels))]).astype(np.int64)
+    # leaf rows: BFS order, tiles, sampled full tiles first, the partial last tile last
+    leaves = np.nonzero(is_leaf)[0]
+    n_leaf = len(leaves)
+    n_full = n_leaf // tile
+    tiles = np.arange(n_full)
+    sampled = tiles[tiles % sample_every == 0] if n_full >= sample_every else tiles[:0]
+    rest = np.setdiff1d(tiles, sampled)
+    perm_tiles = np.concatenate([sampled, rest])
+    idx = (perm_tiles[:, None] * tile + np.arange(tile)[None, :]).reshape(-1)
+    idx = np.concatenate([idx, np.arange(n_full * tile, n_leaf)]).astype(np.int64)
+    leaf_rows = leaves[idx]
+    leaf_len = depth[leaf_rows] + 1
+    leaf_parent = np.where(parent_b[leaf_rows] >= 0, int_of_row[np.maximum(parent_b[leaf_rows], 0)], -1)
+    leaf_w = wrow[leaf_len - 1].astype(np.float32)
+    leaf_inv_len = (1.0 / leaf_len).astype(np.float32)
+    # sentences per leaf (new leaf order), ascending ids
+    new_of_row = np.full(nn, -1, np.int64)
+    new_of_row[leaf_rows] = np.arange(n_leaf)
+    sent_leaf = new_of_row[leaf_row_of_sent]
+    so = np.lexsort((sids, sent_leaf))
+    sent_ids = sids[so]
+    sent_off = np.concatenate([[0], np.cumsum(np.bincount(sent_leaf, minlength=n_leaf))]).astype(np.int64)
+    # flat index over the sentences of the sampled leaves
+    n_s_rows = len(sampled) * tile
+    n_pos_s = int(sent_off[n_s_rows])
+    flat_leaf = sent_leaf[so][:n_pos_s]
+    same = np.zeros(n_pos_s, np.int64)
+    if n_pos_s > 1:
+        same[1:] = flat_leaf[1:] == flat_leaf[:-1]
+    flat_pos_rec = np.stack([np.ones(n_pos_s, np.int64), same, flat_leaf, sent_ids[:n_pos_s]], axis=1).astype(np.int32)
+    return dict(int_rows=int_rows, int_parent=int_parent.astype(np.int32), int_w=int_w, level_off=level_off,
+                leaf_rows=leaf_rows, leaf_parent=leaf_parent.astype(np.int32), leaf_w=leaf_w, leaf_inv_len=leaf_inv_len,
+                n_sample_tiles=int(len(sampled)), sent_off=sent_off.astype(np.int32), sent_ids=sent_ids.astype(np.int32),
+                flat_pos_rec=np.ascontiguousarray(flat_pos_rec), flat_path=flat_leaf.astype(np.int32).reshape(-1, 1),
+                max_len=max_len)

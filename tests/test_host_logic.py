@@ -262,3 +262,44 @@ def test_evaluator_matches_the_reference_loop():
     for key, v in want.items():
         assert got[key] == round(v / nq, 4), key
     assert got["method"] == "x" and got["time_taken"] == 1.5 and got["avg_latency_ms"] == 5.0
+
+
+def test_fused_layout_reproduces_the_path_sums():
+    """(C[parent] + w_leaf s_leaf) / len over the fused layout == sum_j (w_j / len) s_j over the root->leaf paths
+    (CobwebWrapper.py:160-169), every sentence appears exactly once, sampled tiles lead."""
+    rng = np.random.default_rng(3)
+    n_nodes = 4000
+    parent = np.full(n_nodes, -1, np.int64)
+    for i in range(1, n_nodes):
+        parent[i] = rng.integers(max(0, i - 60), i)
+    child_cnt = np.bincount(parent[1:], minlength=n_nodes).astype(np.int32)
+    child_off = (np.cumsum(child_cnt) - child_cnt).astype(np.int32)
+    pool = np.argsort(parent[1:], kind="stable").astype(np.int32) + 1
+    order, parent_b, depth = topology.bfs_order(0, child_off, child_cnt, pool)
+    leaves = np.nonzero(child_cnt == 0)[0]
+    leaf_of_sentence = np.concatenate([leaves, leaves[:37], leaves[:5]])  # some leaves hold two or three sentences
+    leaf_of_sentence = leaf_of_sentence[rng.permutation(len(leaf_of_sentence))]
+    lw = [1.0, 0.5, 2.0, 1.5]
+    F = topology.fused_layout(order, parent_b, depth, leaf_of_sentence, lw, n_slots=n_nodes, tile=64, sample_every=4)
+    s = rng.standard_normal(len(order))                       # one query's node scores by index row
+    C = np.zeros(len(F["int_rows"]))
+    for lvl in range(len(F["level_off"]) - 1):                # top-down, one level at a time
+        a, b = F["level_off"][lvl], F["level_off"][lvl + 1]
+        par = F["int_parent"][a:b]
+        C[a:b] = np.where(par >= 0, C[np.maximum(par, 0)], 0.0) + F["int_w"][a:b].astype(np.float64) * s[F["int_rows"][a:b]]
+    par = F["leaf_parent"]
+    leaf_score = (np.where(par >= 0, C[np.maximum(par, 0)], 0.0) + F["leaf_w"].astype(np.float64) * s[F["leaf_rows"]]) * \
+        F["leaf_inv_len"].astype(np.float64)
+    P = topology.sentence_paths(order, parent_b, depth, leaf_of_sentence, lw, n_slots=n_nodes)
+    want = np.zeros(len(leaf_of_sentence))
+    for p in range(len(leaf_of_sentence)):
+        ln = P["path_len"][p]
+        want[P["pos_sid"][p]] = sum(P["level_w"][j] / ln * s[P["path_idx"][j, p]] for j in range(ln))
+    got = np.full(len(leaf_of_sentence), np.nan)
+    for leaf in range(len(F["leaf_rows"])):
+        got[F["sent_ids"][F["sent_off"][leaf]:F["sent_off"][leaf + 1]]] = leaf_score[leaf]
+    np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-9)
+    assert sorted(F["sent_ids"].tolist()) == list(range(len(leaf_of_sentence)))
+    ns = F["n_sample_tiles"]
+    assert ns == len(range(0, len(F["leaf_rows"]) // 64, 4)) and len(F["flat_pos_rec"]) == F["sent_off"][ns * 64]
+    assert (F["flat_pos_rec"][:, 2] < ns * 64).all() and (np.diff(F["flat_pos_rec"][:, 2]) >= 0).all()
