@@ -209,7 +209,7 @@ def _run_engine(args, wl):
     torch.cuda.synchronize()
     index_build_s = time.time() - t0
     ix = w._index
-    tensor = args.mode == "tf32x3" and ix.candidates(k) > 0
+    tensor = args.mode in ("tf32x3", "tf32x3f") and ix.candidates(k) > 0
     # this rank's batch: global batch = world * qn, contiguous shards
     q_all, targets_all = synth.queries(x, qn * world, kind, seed=1, targets=np.arange(qn * world) % docs)
     lo, hi = parallel.shard_bounds(qn * world, world, rank)
@@ -483,7 +483,7 @@ def main():
     ap.add_argument("--docs", type=int)
     ap.add_argument("--queries", type=int)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--mode", default="tf32x3", choices=["tf32x3", "fp32"],
+    ap.add_argument("--mode", default="tf32x3", choices=["tf32x3", "tf32x3f", "fp32"],
                     help="node scores on the tensor cores (tcgen05 split-TF32 pre-filter + exact FP32 re-score, default) "
                          "or on the FP32 pipe; the results are identical")
     ap.add_argument("--shard", default="query", choices=["query", "store"],

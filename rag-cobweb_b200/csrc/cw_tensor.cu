@@ -164,10 +164,32 @@ __device__ __forceinline__ void tile_coords(long long t, int n_qtiles, int n_nti
     qt = p * pq + (int)(rem % w);
 }
 
+// What the epilogue does with a finished 128 x 256 accumulator (lane = query, column = index row):
+//   EPI_NODE    node score s = h - 0.5 acc, written node-major                              (all rows of an index)
+//   EPI_LEAF    leaf score (C[parent] + w s) / len from the cumulative ancestor sums C,
+//               written row-major                                           (the sampled leaf tiles of "tf32x3f")
+//   EPI_FILTER  the same leaf score, appended to the query's candidate buffer when it reaches the query's
+//               threshold tau; nothing else is written                          (the other leaf tiles of "tf32x3f")
+enum { EPI_NODE = 0, EPI_LEAF = 1, EPI_FILTER = 2 };
+struct TcEpi {
+    float *out;              // NODE / LEAF: [rows, ldq]
+    long long ldq;
+    const float *hconst;     // NODE: per row
+    const float4 *leaf_rec;  // LEAF / FILTER: per leaf row {h, w_leaf, 1/len, parent internal row as int bits}
+    const float *C;          // LEAF / FILTER: [internal rows, ldq]
+    int n_rows;              // FILTER: real rows of this index (the rest is tile padding)
+    long long nq;            // FILTER
+    const float *tau;        // FILTER: [nq]
+    int cap;                 // FILTER: candidate slots per query
+    int *cnt;                // FILTER: [nq] candidates appended (may exceed cap: overflow)
+    float *cand_val;         // FILTER: [nq, cap]
+    int *cand_row;           // FILTER: [nq, cap]
+};
+
+template <int MODE>
 __global__ void __launch_bounds__(THREADS, 1)
-tc_score_kernel(const unsigned char *__restrict__ A, const unsigned char *__restrict__ B,
-                const float *__restrict__ hconst, float *__restrict__ out, long long ldq, int n_qtiles, int n_ntiles,
-                int n_slabs, int pq) {
+tc_score_kernel(const unsigned char *__restrict__ A, const unsigned char *__restrict__ B, const TcEpi epi, int n_qtiles,
+                int nt_begin, int n_ntiles, int n_slabs, int pq) {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // swizzle atoms need their natural alignment
     const uint32_t bars = base + NSTAGE * STAGE_BYTES;
@@ -206,7 +228,7 @@ tc_score_kernel(const unsigned char *__restrict__ A, const unsigned char *__rest
                 int nt, qt;
                 tile_coords(t, n_qtiles, n_ntiles, pq, nt, qt);
                 const unsigned char *asrc = A + (size_t)qt * n_slabs * A_BYTES;
-                const unsigned char *bsrc = B + (size_t)nt * n_slabs * B_BYTES;
+                const unsigned char *bsrc = B + (size_t)(nt_begin + nt) * n_slabs * B_BYTES;
                 for (int s = 0; s < n_slabs; s++) {
                     mbar_wait(empty0 + 8 * stage, phase ^ 1);
                     const uint32_t sb = base + stage * STAGE_BYTES;
@@ -262,13 +284,20 @@ tc_score_kernel(const unsigned char *__restrict__ A, const unsigned char *__rest
             tile_coords(t, n_qtiles, n_ntiles, pq, nt, qt);
             mbar_wait(accf, aphase);
             tc_fence_after();
-            const long long n0 = (long long)nt * TN;
+            const long long n0 = (long long)(nt_begin + nt) * TN;
+            const long long ldq = epi.ldq;
 #pragma unroll 1
             for (int qh = 0; qh < 2; qh++) {
                 const long long q0 = (long long)qt * TQ + qh * TM;
                 if (q0 >= ldq) break;  // a half-tile of pure padding past the score matrix
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(qh * TN);
-                float *col = out + q0 + quarter * 32 + lane;
+                const long long q = q0 + quarter * 32 + lane;
+                float tau = 0.0f;
+                bool live = false;
+                if (MODE == EPI_FILTER) {
+                    live = q < epi.nq;
+                    if (live) tau = epi.tau[q];
+                }
 #pragma unroll 1
                 for (int c = 0; c < TN / 32; c++) {
                     uint32_t v[32];
@@ -277,7 +306,24 @@ tc_score_kernel(const unsigned char *__restrict__ A, const unsigned char *__rest
 #pragma unroll
                     for (int j = 0; j < 32; j++) {
                         const long long n = n0 + c * 32 + j;
-                        col[n * ldq] = fmaf(-0.5f, __uint_as_float(v[j]), __ldg(hconst + n));
+                        if (MODE == EPI_NODE) {
+                            epi.out[n * ldq + q] = fmaf(-0.5f, __uint_as_float(v[j]), __ldg(epi.hconst + n));
+                        } else {
+                            const float4 r = __ldg(epi.leaf_rec + n);  // uniform: one broadcast load per row
+                            const int par = __float_as_int(r.w);
+                            const float s = fmaf(-0.5f, __uint_as_float(v[j]), r.x);
+                            const float cp = par >= 0 ? __ldg(epi.C + (long long)par * ldq + q) : 0.0f;
+                            const float score = fmaf(r.y, s, cp) * r.z;
+                            if (MODE == EPI_LEAF) {
+                                epi.out[n * ldq + q] = score;
+                            } else if (live && n < epi.n_rows && score >= tau) {
+                                const int at = atomicAdd(epi.cnt + q, 1);
+                                if (at < epi.cap) {
+                                    epi.cand_val[q * epi.cap + at] = score;
+                                    epi.cand_row[q * epi.cap + at] = (int)n;
+                                }
+                            }
+                        }
                     }
                 }
             }
@@ -416,23 +462,81 @@ extern "C" int cw_tc_index_build(const cw_store *s, const int32_t *order, int32_
     return cw_check_cuda(cudaGetLastError(), "cw_tc_index_build");
 }
 
-extern "C" int cw_dense_node_scores_tc(const cw_tc_index *tx, const float *Q, int64_t nq, void *a_scratch,
-                                       float *node_scores, int64_t ldq, void *stream) {
-    if (!tx || !Q || !a_scratch || !node_scores || nq < 0 || ldq < cw_score_ldq(nq) || (ldq % TM)) {
-        cw_set_error("cw_dense_node_scores_tc: bad argument (ldq must be >= cw_score_ldq(nq) and a multiple of %d)", TM);
-        return CW_E_ARG;
+// C[n][q] = C[parent(n)][q] + w_n * S[n][q] for the internal rows of one tree level, in place on S
+__global__ void __launch_bounds__(256)
+tc_cumsum_kernel(float *S, long long ldq, int row_begin, int row_end, const int *__restrict__ int_parent,
+                 const float *__restrict__ int_w) {
+    const long long per_row = ldq >> 2;
+    const long long total = (long long)(row_end - row_begin) * per_row;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int n = row_begin + (int)(i / per_row);
+        const long long q4 = (i % per_row) << 2;
+        const int par = int_parent[n];
+        const float w = int_w[n];
+        float4 s = *reinterpret_cast<float4 *>(S + (long long)n * ldq + q4);
+        float4 c = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (par >= 0) c = *reinterpret_cast<const float4 *>(S + (long long)par * ldq + q4);
+        s.x = fmaf(w, s.x, c.x); s.y = fmaf(w, s.y, c.y); s.z = fmaf(w, s.z, c.z); s.w = fmaf(w, s.w, c.w);
+        *reinterpret_cast<float4 *>(S + (long long)n * ldq + q4) = s;
     }
-    if (nq == 0) return 0;
-    cudaStream_t st = (cudaStream_t)stream;
+}
+
+// Final candidate list of a query: the top-kc of the sampled leaves (sentence ids) united with the leaves the
+// filter appended (expanded to their sentences), best kc by (score desc, sentence id asc).  One CTA per query.
+constexpr int SEL_MAX = 2048;
+__global__ void __launch_bounds__(128)
+tc_select_kernel(long long nq, int kc, const int *__restrict__ samp_sid, const float *__restrict__ samp_val, int cap,
+                 const int *__restrict__ cnt, const float *__restrict__ cand_val, const int *__restrict__ cand_row,
+                 const int *__restrict__ sent_off, const int *__restrict__ sent_ids, int *out_sid, float *out_val, int *ovf) {
+    __shared__ float vals[SEL_MAX];
+    __shared__ int sids[SEL_MAX];
+    __shared__ int total;
+    const int tid = threadIdx.x;
+    for (long long q = blockIdx.x; q < nq; q += gridDim.x) {
+        __syncthreads();
+        if (tid == 0) total = 0;
+        __syncthreads();
+        if (tid < kc && samp_sid && samp_sid[q * kc + tid] >= 0) {
+            const int at = atomicAdd(&total, 1);
+            vals[at] = samp_val[q * kc + tid];
+            sids[at] = samp_sid[q * kc + tid];
+        }
+        const int n_app = min(cnt[q], cap);
+        bool over = cnt[q] > cap;
+        for (int i = tid; i < n_app; i += blockDim.x) {
+            const int row = cand_row[q * cap + i];
+            const float v = cand_val[q * cap + i];
+            const int s0 = sent_off[row], s1 = sent_off[row + 1];
+            const int at = atomicAdd(&total, s1 - s0);
+            for (int s = s0; s < s1; s++)
+                if (at + (s - s0) < SEL_MAX) { vals[at + (s - s0)] = v; sids[at + (s - s0)] = sent_ids[s]; }
+        }
+        __syncthreads();
+        const int n = min(total, SEL_MAX);
+        over = over || total > SEL_MAX;
+        if (tid == 0) ovf[q] = over ? 1 : 0;
+        for (int i = tid; i < n; i += blockDim.x) {
+            const float v = vals[i];
+            const int sid = sids[i];
+            int rank = 0;
+            for (int j = 0; j < n && rank < kc; j++) rank += vals[j] > v || (vals[j] == v && sids[j] < sid);
+            if (rank < kc) { out_sid[q * kc + rank] = sid; out_val[q * kc + rank] = v; }
+        }
+        for (int r = n + tid; r < kc; r += blockDim.x) { out_sid[q * kc + r] = -1; out_val[q * kc + r] = -__int_as_float(0x7f800000); }
+    }
+}
+
+static int tc_launch(int mode, const cw_tc_index *tx, const void *a_scratch, int64_t nq, int nt_begin, int nt_count,
+                     const TcEpi &epi, cudaStream_t st) {
     const int n_qtiles = (int)((nq + TQ - 1) / TQ);
-    int rc = cw_check_cuda(cudaFuncSetAttribute(tc_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES),
-                           "cw_dense_node_scores_tc: smem attribute");
+    auto kern = mode == EPI_NODE ? tc_score_kernel<EPI_NODE> : (mode == EPI_LEAF ? tc_score_kernel<EPI_LEAF> : tc_score_kernel<EPI_FILTER>);
+    int rc = cw_check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES),
+                           "cw_tc: smem attribute");
     if (rc) return rc;
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    tc_queries_kernel<<<dim3(n_qtiles, tx->n_slabs), 256, 0, st>>>(Q, nq, tx->D, tx->n_slabs,
-                                                                  reinterpret_cast<unsigned char *>(a_scratch));
-    const long long n_tiles = (long long)n_qtiles * tx->n_ntiles;
+    const long long n_tiles = (long long)n_qtiles * nt_count;
+    if (n_tiles == 0) return 0;
     const int grid = (int)(n_tiles < sms ? n_tiles : sms);
     // query-tile panels: the panel's query operands (A_BYTES per tile and slab) should sit in L2 (~40 MB of it)
     // while the node operands stream through; equal-width panels
@@ -441,8 +545,88 @@ extern "C" int cw_dense_node_scores_tc(const cw_tc_index *tx, const float *Q, in
     if (pq_max < 1) pq_max = 1;
     const int n_panels = (n_qtiles + pq_max - 1) / pq_max;
     const int pq = (n_qtiles + n_panels - 1) / n_panels;
-    tc_score_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(reinterpret_cast<const unsigned char *>(a_scratch),
-                                                       reinterpret_cast<const unsigned char *>(tx->B), tx->hconst,
-                                                       node_scores, ldq, n_qtiles, tx->n_ntiles, tx->n_slabs, pq);
-    return cw_check_cuda(cudaGetLastError(), "cw_dense_node_scores_tc");
+    kern<<<grid, THREADS, SMEM_BYTES, st>>>(reinterpret_cast<const unsigned char *>(a_scratch),
+                                            reinterpret_cast<const unsigned char *>(tx->B), epi, n_qtiles, nt_begin, nt_count,
+                                            tx->n_slabs, pq);
+    return cw_check_cuda(cudaGetLastError(), "cw_tc: score kernel");
+}
+
+extern "C" int cw_tc_build_queries(const cw_tc_index *tx, const float *Q, int64_t nq, void *a_scratch, void *stream) {
+    if (!tx || !Q || !a_scratch || nq < 0) {
+        cw_set_error("cw_tc_build_queries: bad argument");
+        return CW_E_ARG;
+    }
+    if (nq == 0) return 0;
+    const int n_qtiles = (int)((nq + TQ - 1) / TQ);
+    tc_queries_kernel<<<dim3(n_qtiles, tx->n_slabs), 256, 0, (cudaStream_t)stream>>>(Q, nq, tx->D, tx->n_slabs,
+                                                                                    reinterpret_cast<unsigned char *>(a_scratch));
+    return cw_check_cuda(cudaGetLastError(), "cw_tc_build_queries");
+}
+
+extern "C" int cw_tc_score_tiles(const cw_tc_index *tx, const void *a_scratch, int64_t nq, int mode, int32_t nt_begin,
+                                 int32_t nt_count, float *out, int64_t ldq, const float *C, const float *leaf_rec,
+                                 int32_t n_rows, const float *tau, int32_t cap, int32_t *cnt, float *cand_val,
+                                 int32_t *cand_row, void *stream) {
+    if (!tx || !a_scratch || nq < 0 || ldq < cw_score_ldq(nq) || (ldq % TM) || mode < EPI_NODE || mode > EPI_FILTER ||
+        nt_begin < 0 || nt_count < 0 || nt_begin + nt_count > tx->n_ntiles || (mode != EPI_FILTER && !out) ||
+        (mode != EPI_NODE && (!C || !leaf_rec)) || (mode == EPI_FILTER && (!tau || !cnt || !cand_val || !cand_row || cap < 1))) {
+        cw_set_error("cw_tc_score_tiles: bad argument (mode %d, tiles %d+%d of %d)", mode, nt_begin, nt_count, tx ? tx->n_ntiles : -1);
+        return CW_E_ARG;
+    }
+    if (nq == 0) return 0;
+    TcEpi epi;
+    epi.out = out;
+    epi.ldq = ldq;
+    epi.hconst = tx->hconst;
+    epi.leaf_rec = reinterpret_cast<const float4 *>(leaf_rec);
+    epi.C = C;
+    epi.n_rows = n_rows;
+    epi.nq = nq;
+    epi.tau = tau;
+    epi.cap = cap;
+    epi.cnt = cnt;
+    epi.cand_val = cand_val;
+    epi.cand_row = cand_row;
+    return tc_launch(mode, tx, a_scratch, nq, nt_begin, nt_count, epi, (cudaStream_t)stream);
+}
+
+extern "C" int cw_tc_cumsum_level(float *S, int64_t ldq, int32_t row_begin, int32_t row_end, const int32_t *int_parent,
+                                  const float *int_w, void *stream) {
+    if (!S || !int_parent || !int_w || (ldq & 3) || row_begin < 0 || row_end < row_begin) {
+        cw_set_error("cw_tc_cumsum_level: bad argument");
+        return CW_E_ARG;
+    }
+    if (row_end == row_begin) return 0;
+    const long long total = (long long)(row_end - row_begin) * (ldq >> 2);
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    tc_cumsum_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(S, ldq, row_begin, row_end, int_parent, int_w);
+    return cw_check_cuda(cudaGetLastError(), "cw_tc_cumsum_level");
+}
+
+extern "C" int cw_tc_select(int64_t nq, int kc, const int32_t *samp_sid, const float *samp_val, int32_t cap,
+                            const int32_t *cnt, const float *cand_val, const int32_t *cand_row, const int32_t *sent_off,
+                            const int32_t *sent_ids, int32_t *out_sid, float *out_val, int32_t *ovf, void *stream) {
+    if (nq < 0 || kc < 1 || kc > 128 || cap < 1 || !cnt || !cand_val || !cand_row || !sent_off || !sent_ids || !out_sid ||
+        !out_val || !ovf || (samp_sid && !samp_val)) {
+        cw_set_error("cw_tc_select: bad argument");
+        return CW_E_ARG;
+    }
+    if (nq == 0) return 0;
+    tc_select_kernel<<<(unsigned)(nq < 148 * 16 ? nq : 148 * 16), 128, 0, (cudaStream_t)stream>>>(
+        nq, kc, samp_sid, samp_val, cap, cnt, cand_val, cand_row, sent_off, sent_ids, out_sid, out_val, ovf);
+    return cw_check_cuda(cudaGetLastError(), "cw_tc_select");
+}
+
+extern "C" int cw_dense_node_scores_tc(const cw_tc_index *tx, const float *Q, int64_t nq, void *a_scratch,
+                                       float *node_scores, int64_t ldq, void *stream) {
+    if (!tx || !Q || !a_scratch || !node_scores || nq < 0 || ldq < cw_score_ldq(nq) || (ldq % TM)) {
+        cw_set_error("cw_dense_node_scores_tc: bad argument (ldq must be >= cw_score_ldq(nq) and a multiple of %d)", TM);
+        return CW_E_ARG;
+    }
+    if (nq == 0) return 0;
+    int rc = cw_tc_build_queries(tx, Q, nq, a_scratch, stream);
+    if (rc) return rc;
+    return cw_tc_score_tiles(tx, a_scratch, nq, EPI_NODE, 0, tx->n_ntiles, node_scores, ldq, nullptr, nullptr, 0, nullptr, 0,
+                             nullptr, nullptr, nullptr, stream);
 }

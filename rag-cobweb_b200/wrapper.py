@@ -32,7 +32,11 @@ class DenseIndex:
     # "tf32x3" = tcgen05 contraction with hi/lo-split TF32 operands (cw_tensor.cu, ~1e-6 relative to "fp32") as a
     # pre-filter for top-kc candidates, followed by the exact re-score (cw_rescore.cu): top-k ids and scores are
     # bit-identical to "fp32"; raw node / leaf score matrices in this mode are the approximate ones
-    MODES = ("fp32", "tf32x3")
+    # "tf32x3f" = the same pre-filter with the path sums fused into the score kernel (cumulative ancestor sums +
+    # leaf scores in the epilogue, candidates filtered against a per-query bound from a sample of the leaves): the
+    # [nodes, queries] score matrix and the path kernel disappear for the leaves; same exact re-score, same results
+    MODES = ("fp32", "tf32x3", "tf32x3f")
+    FUSED_CAP = 1024  # candidate slots per query of the filtering epilogue
     EPS_SCALE = 2.0 ** -18  # bound of |tf32x3 - fp32| leaf score relative to the operand magnitudes (cw_dense_rescore)
 
     def __init__(self, tree, leaf_of_sentence, level_weights=None, sentence_ids=None):
@@ -51,6 +55,7 @@ class DenseIndex:
             leaf_of_sentence = leaf_of_sentence[self.sentence_ids]
             order, parent_b, depth = topology.restrict_to_paths(order, parent_b, depth, leaf_of_sentence, t["n_used"])
         self.order_host = order
+        self._topo = (parent_b, depth, leaf_of_sentence, level_weights, t["n_used"])
         self.nn = len(order)
         self.max_depth = int(depth.max()) + 1
         d = tree.d
@@ -90,6 +95,14 @@ class DenseIndex:
         operands (cw_tc_index_build) on first use."""
         if mode not in self.MODES:
             raise ValueError(f"mode must be one of {self.MODES}")
+        if mode == "tf32x3f":
+            self.set_mode("tf32x3")
+            if not self.n_pos:
+                return self
+            if getattr(self, "fx", None) is None:
+                self._build_fused()
+            self.mode = mode
+            return self
         if mode == "tf32x3" and self.tx is None:
             L, dev, d = _lib.load(), self.tree.device, self.tree.d
             tx = _lib.CwTcIndex()
@@ -124,9 +137,119 @@ class DenseIndex:
         self.mode = mode
         return self
 
+    def _build_fused(self):
+        """Operands of the fused mode: separate score-kernel operand sets for the internal and the leaf rows
+        (topology.fused_layout), per-leaf records, the flat index over the sampled leaves."""
+        L, dev, d = _lib.load(), self.tree.device, self.tree.d
+        parent_b, depth, leaf_of_sentence, level_weights, n_used = self._topo
+        F = topology.fused_layout(self.order_host, parent_b, depth, leaf_of_sentence, level_weights, n_slots=n_used,
+                                  sentence_ids=self.sentence_ids, tile=_lib.TC_TILE_N)
+        order_np = np.asarray(self.order_host, np.int64)
+        fx = {"F": F, "n_int": len(F["int_rows"]), "n_leaf": len(F["leaf_rows"]), "n_s": F["n_sample_tiles"]}
+
+        def tc_index(rows):
+            tx = _lib.CwTcIndex()
+            tx.D, tx.nn = d, len(rows)
+            tx.n_ntiles = (len(rows) + _lib.TC_TILE_N - 1) // _lib.TC_TILE_N
+            tx.n_slabs = (d + _lib.TC_SLAB_D - 1) // _lib.TC_SLAB_D
+            B = torch.empty(L.cw_tc_b_bytes(len(rows), d), dtype=torch.uint8, device=dev)
+            h = torch.empty(tx.n_ntiles * _lib.TC_TILE_N, dtype=torch.float32, device=dev)
+            od = torch.as_tensor(order_np[rows].astype(np.int32), device=dev)
+            sl = self.sumlog[torch.as_tensor(rows, device=dev)].contiguous()
+            tx.B, tx.hconst = B.data_ptr(), h.data_ptr()
+            _lib.check(L.cw_tc_index_build(self.tree.store.struct(), od.data_ptr(), len(rows), sl.data_ptr(), C.byref(tx),
+                                           _lib.stream_ptr()), "cw_tc_index_build")
+            torch.cuda.current_stream().synchronize()  # od / sl may be freed after this
+            return tx, B, h
+
+        if fx["n_int"]:
+            fx["tx_int"], fx["B_int"], fx["h_int"] = tc_index(F["int_rows"])
+            fx["int_parent"] = torch.as_tensor(F["int_parent"], device=dev)
+            fx["int_w"] = torch.as_tensor(F["int_w"], device=dev)
+        fx["tx_leaf"], fx["B_leaf"], fx["h_leaf"] = tc_index(F["leaf_rows"])
+        n_pad = fx["tx_leaf"].n_ntiles * _lib.TC_TILE_N
+        rec = torch.zeros((n_pad, 4), dtype=torch.float32, device=dev)
+        nl = fx["n_leaf"]
+        rec[:nl, 0] = fx["h_leaf"][:nl]
+        rec[:nl, 1] = torch.as_tensor(F["leaf_w"], device=dev)
+        rec[:nl, 2] = torch.as_tensor(F["leaf_inv_len"], device=dev)
+        par = torch.full((n_pad,), -1, dtype=torch.int32, device=dev)
+        par[:nl] = torch.as_tensor(F["leaf_parent"], device=dev)
+        rec[:, 3] = par.view(torch.float32)
+        fx["leaf_rec"] = rec
+        fx["sent_off"] = torch.as_tensor(F["sent_off"], device=dev)
+        fx["sent_ids"] = torch.as_tensor(F["sent_ids"], device=dev)
+        if fx["n_s"]:
+            flat = _lib.CwIndex()
+            flat.D, flat.nn, flat.n_pos, flat.max_len = d, fx["n_s"] * _lib.TC_TILE_N, len(F["flat_pos_rec"]), 1
+            fx["flat_path"] = torch.as_tensor(F["flat_path"], device=dev)
+            fx["flat_rec"] = torch.as_tensor(F["flat_pos_rec"], device=dev)
+            fx["flat_w"] = torch.ones(1, dtype=torch.float64, device=dev)
+            flat.path_idx, flat.pos_rec, flat.level_w = fx["flat_path"].data_ptr(), fx["flat_rec"].data_ptr(), fx["flat_w"].data_ptr()
+            fx["flat"] = flat
+        self.fx = fx
+
+    def _fused_candidates(self, q, nq, kc, ws):
+        """Top-kc candidates (sentence ids + approximate leaf scores, best first) of the fused mode into
+        ws["cand_sid"] / ws["cand_val"]; returns the overflow flags [nq]."""
+        L, fx, dev = _lib.load(), self.fx, self.tree.device
+        T, ldq, st = _lib.TC_TILE_N, ws["ldq"], _lib.stream_ptr()
+        n_int_pad = (fx["n_int"] + T - 1) // T * T
+        n_s_rows = fx["n_s"] * T
+        scores = ws["scores"]
+        if scores.shape[0] < n_int_pad + n_s_rows:
+            ws["fused_extra"] = ws.get("fused_extra") if ws.get("fused_extra") is not None and ws["fused_extra"].shape[0] >= n_s_rows \
+                else torch.empty((max(n_s_rows, 1), ldq), dtype=torch.float32, device=dev)
+            LS = ws["fused_extra"]
+        else:
+            LS = scores[n_int_pad:n_int_pad + max(n_s_rows, 1)]
+        S = scores[:max(n_int_pad, 1)]
+        cap = self.FUSED_CAP
+        if ws.get("f_cap_q", 0) < nq:
+            ws["f_val"] = torch.empty((ws["cap_q"], cap), dtype=torch.float32, device=dev)
+            ws["f_row"] = torch.empty((ws["cap_q"], cap), dtype=torch.int32, device=dev)
+            ws["f_cnt"] = torch.zeros(ws["cap_q"], dtype=torch.int32, device=dev)
+            ws["f_ovf"] = torch.zeros(ws["cap_q"], dtype=torch.int32, device=dev)
+            ws["f_samp_sid"] = torch.empty((ws["cap_q"], ws["cand_sid"].shape[1]), dtype=torch.int32, device=dev)
+            ws["f_samp_val"] = torch.empty((ws["cap_q"], ws["cand_sid"].shape[1]), dtype=torch.float32, device=dev)
+            ws["f_cap_q"] = ws["cap_q"]
+        tx_leaf = fx["tx_leaf"]
+        _lib.check(L.cw_tc_build_queries(C.byref(tx_leaf), q.data_ptr(), nq, ws["xt"].data_ptr(), st), "cw_tc_build_queries")
+        if fx["n_int"]:
+            tx_int = fx["tx_int"]
+            _lib.check(L.cw_tc_score_tiles(C.byref(tx_int), ws["xt"].data_ptr(), nq, 0, 0, tx_int.n_ntiles, S.data_ptr(), ldq,
+                                           None, None, 0, None, 0, None, None, None, st), "cw_tc_score_tiles (internal)")
+            off = fx["F"]["level_off"]
+            for lvl in range(len(off) - 1):
+                _lib.check(L.cw_tc_cumsum_level(S.data_ptr(), ldq, int(off[lvl]), int(off[lvl + 1]), fx["int_parent"].data_ptr(),
+                                                fx["int_w"].data_ptr(), st), "cw_tc_cumsum_level")
+        tau = torch.full((nq,), float("-inf"), dtype=torch.float32, device=dev)
+        samp_sid = samp_val = None
+        if fx["n_s"]:
+            _lib.check(L.cw_tc_score_tiles(C.byref(tx_leaf), ws["xt"].data_ptr(), nq, 1, 0, fx["n_s"], LS.data_ptr(), ldq,
+                                           S.data_ptr(), fx["leaf_rec"].data_ptr(), fx["n_leaf"], None, 0, None, None, None, st),
+                       "cw_tc_score_tiles (sample)")
+            samp_sid, samp_val = ws["f_samp_sid"], ws["f_samp_val"]
+            _lib.check(L.cw_dense_paths_topk(C.byref(fx["flat"]), LS.data_ptr(), ldq, nq, kc, None, samp_sid.data_ptr(),
+                                             samp_val.data_ptr(), ws["scratch"].data_ptr(), st), "cw_dense_paths_topk (sample)")
+            sv = samp_val.view(-1)[: nq * kc].view(nq, kc)
+            ss = samp_sid.view(-1)[: nq * kc].view(nq, kc)
+            tau = torch.where(ss[:, kc - 1] >= 0, sv[:, kc - 1], tau)
+        ws["f_cnt"][:nq].zero_()
+        _lib.check(L.cw_tc_score_tiles(C.byref(tx_leaf), ws["xt"].data_ptr(), nq, 2, fx["n_s"], tx_leaf.n_ntiles - fx["n_s"], None,
+                                       ldq, S.data_ptr(), fx["leaf_rec"].data_ptr(), fx["n_leaf"], tau.data_ptr(), cap,
+                                       ws["f_cnt"].data_ptr(), ws["f_val"].data_ptr(), ws["f_row"].data_ptr(), st),
+                   "cw_tc_score_tiles (filter)")
+        _lib.check(L.cw_tc_select(nq, kc, samp_sid.data_ptr() if samp_sid is not None else None,
+                                  samp_val.data_ptr() if samp_val is not None else None, cap, ws["f_cnt"].data_ptr(),
+                                  ws["f_val"].data_ptr(), ws["f_row"].data_ptr(), fx["sent_off"].data_ptr(),
+                                  fx["sent_ids"].data_ptr(), ws["cand_sid"].data_ptr(), ws["cand_val"].data_ptr(),
+                                  ws["f_ovf"].data_ptr(), st), "cw_tc_select")
+        return ws["f_ovf"][:nq]
+
     def _node_scores_call(self, q, nq, ws):
         L = _lib.load()
-        if self.mode == "tf32x3":
+        if self.mode in ("tf32x3", "tf32x3f"):
             _lib.check(L.cw_dense_node_scores_tc(C.byref(self.tx), q.data_ptr(), nq, ws["xt"].data_ptr(),
                                                  ws["scores"].data_ptr(), ws["ldq"], _lib.stream_ptr()), "cw_dense_node_scores_tc")
         else:
@@ -223,9 +346,11 @@ class DenseIndex:
                 return self.predict(Q, k, want_leaf_scores)
             finally:
                 self.mode = prev
-        kc = self.candidates(k, _level) if (mode == "tf32x3" and not want_leaf_scores) else 0
-        if mode == "tf32x3" and kc == 0 and k > 0 and not want_leaf_scores:
+        tensor = mode in ("tf32x3", "tf32x3f")
+        kc = self.candidates(k, _level) if (tensor and not want_leaf_scores) else 0
+        if tensor and kc == 0 and k > 0 and not want_leaf_scores:
             return self.predict(Q, k, mode="fp32")  # this k / depth is not served by the re-score kernel
+        fused = mode == "tf32x3f" and kc > 0 and _level == 0 and getattr(self, "fx", None) is not None
         nq_total = Q.shape[0]
         step = self.chunk_queries()
         sids = torch.empty((nq_total, max(k, 1)), dtype=torch.int32, device=Q.device)
@@ -236,19 +361,27 @@ class DenseIndex:
             nq = min(step, nq_total - lo)
             ws = self.workspace(min(step, nq_total), k)
             q = Q[lo:lo + nq]
-            self._node_scores_call(q, nq, ws)
+            ovf = None
+            if fused:
+                ovf = self._fused_candidates(q, nq, kc, ws)
+            else:
+                self._node_scores_call(q, nq, ws)
             if kc:
-                _lib.check(L.cw_dense_paths_topk(C.byref(self.ix), ws["scores"].data_ptr(), ws["ldq"], nq, kc, None,
-                                                 ws["cand_sid"].data_ptr(), ws["cand_val"].data_ptr(), ws["scratch"].data_ptr(),
-                                                 _lib.stream_ptr()), "cw_dense_paths_topk")
+                if not fused:
+                    _lib.check(L.cw_dense_paths_topk(C.byref(self.ix), ws["scores"].data_ptr(), ws["ldq"], nq, kc, None,
+                                                     ws["cand_sid"].data_ptr(), ws["cand_val"].data_ptr(),
+                                                     ws["scratch"].data_ptr(), _lib.stream_ptr()), "cw_dense_paths_topk")
                 tx = self.tx
                 _lib.check(L.cw_dense_rescore(self.tree.store.struct(), C.byref(self.ix), tx.rows, tx.pos_of_sid, q.data_ptr(),
                                               nq, kc, ws["cand_sid"].data_ptr(), ws["cand_val"].data_ptr(), k, tx.hmax, tx.lmax,
                                               tx.wfac, tx.eps_scale, sids[lo:lo + nq].data_ptr(), vals[lo:lo + nq].data_ptr(),
                                               ws["fail"].data_ptr(), _lib.stream_ptr()), "cw_dense_rescore")
                 nf = int(ws["fail"][0])  # one 4-byte read-back per chunk
-                if nf:
-                    redo.append(ws["fail"][1:1 + nf].long() + lo)
+                flagged = ws["fail"][1:1 + nf].long()
+                if ovf is not None and bool(ovf.any()):  # candidate buffer overflow: treat like a flagged query
+                    flagged = torch.unique(torch.cat([flagged, torch.nonzero(ovf).view(-1)]))
+                if flagged.numel():
+                    redo.append(flagged + lo)
             else:
                 _lib.check(L.cw_dense_paths_topk(C.byref(self.ix), ws["scores"].data_ptr(), ws["ldq"], nq, k,
                                                  leaf[lo:lo + nq].data_ptr() if leaf is not None else None,
@@ -260,7 +393,7 @@ class DenseIndex:
             idx = torch.cat(redo)
             if self.candidates(k, _level + 1):
                 self.n_escalated += int(idx.numel())
-                s2, v2, _ = self.predict(Q[idx].contiguous(), k, _level=_level + 1)
+                s2, v2, _ = self.predict(Q[idx].contiguous(), k, mode="tf32x3" if fused else None, _level=_level + 1)
             else:
                 self.n_fallback += int(idx.numel())
                 s2, v2, _ = self.predict(Q[idx].contiguous(), k, mode="fp32")
@@ -286,6 +419,18 @@ class DenseIndex:
         if out_sid is None:
             out_sid = torch.empty((nq_total, k), dtype=torch.int32)
             out_val = torch.empty((nq_total, k), dtype=torch.float32)
+        if self.mode == "tf32x3f" and self.candidates(k) > 0:
+            # fused mode: pinned host batch -> device, the device pipeline, ids/scores back (no single C call yet)
+            for lo in range(0, nq_total, step):
+                nq = min(step, nq_total - lo)
+                ws = self.workspace(min(step, nq_total), k)
+                qd = ws["q"][:nq]
+                qd.copy_(Qh[lo:lo + nq], non_blocking=True)
+                sd, vd, _ = self.predict(qd, k)
+                out_sid[lo:lo + nq].copy_(sd, non_blocking=True)
+                out_val[lo:lo + nq].copy_(vd, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return out_sid, out_val
         tensor = self.mode == "tf32x3" and self.candidates(k) > 0
         nfb = (C.c_int32 * 2)(0, 0)
         for lo in range(0, nq_total, step):

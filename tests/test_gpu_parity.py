@@ -572,3 +572,35 @@ def test_batched_evaluator_on_device():
         evaluate_cobweb(w, q[:50], targets[:50], top_k=10, mode="basic")["recall@10"]
     dot = evaluate_dot(x, q, targets, top_k=10)
     assert dot["recall@10"] >= 0.99 and basic["recall@10"] > 0.5
+
+
+@pytest.mark.parametrize("n,d,kind,k,weights", [(6000, 64, "unit", 10, None), (5000, 96, "whitened", 5, [1.0, 0.5, 2.0, 1.5]),
+                                                (700, 128, "unit", 10, None), (3000, 40, "unit", 16, None)])
+def test_fused_tensor_predict_matches_fp32_path(n, d, kind, k, weights):
+    """"tf32x3f": cumulative ancestor sums + leaf scores in the score kernel's epilogue, candidates filtered against
+    a per-query bound from a sample of the leaf tiles (cw_tensor.cu modes 1/2, cw_tc_cumsum_level, cw_tc_select),
+    then the exact re-score: ids and scores bit-identical to the FP32-pipe path.  6000/5000/3000 leaves = sampled
+    tiles exist; 700 = every leaf goes through the filter with an open threshold; duplicated documents = leaves
+    with several sentences."""
+    x = synth.corpus(n, d, kind, seed=11)
+    x[100:130] = x[7]          # a leaf with 31 sentences
+    x[200:203] = x[9]
+    w = CobwebWrapper(corpus=[None] * n, corpus_embeddings=x)
+    if weights is not None:
+        w.set_level_weights(weights)
+    q, _ = synth.queries(x, 517, kind, seed=12)
+    q[:3] = x[[7, 9, 11]] + 1e-3
+    qd = torch.from_numpy(q).cuda()
+    w.build_prediction_index()
+    ix = w._index
+    ids32, v32, _ = ix.predict(qd, k)
+    ix.set_mode("tf32x3f")
+    assert ix.mode == "tf32x3f" and (ix.fx["n_s"] > 0) == (n >= 3000)
+    n0 = ix.n_fallback
+    ids, vals, _ = ix.predict(qd, k)
+    assert torch.equal(ids, ids32) and torch.equal(vals, v32)
+    hs, hv = ix.predict_host(q, k)
+    assert np.array_equal(hs.numpy(), ids32.cpu().numpy()) and np.array_equal(hv.numpy(), v32.cpu().numpy())
+    assert ix.n_fallback - n0 <= 8
+    w.set_dense_mode("tf32x3f")
+    assert w.cobweb_predict_fast(q[5], k=k, return_ids=True, is_embedding=True) == list(ids32[5].cpu().numpy())
