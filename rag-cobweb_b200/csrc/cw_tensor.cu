@@ -51,7 +51,8 @@ constexpr int B_BYTES = 2 * B_IMG;
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;  // 64 KB
 constexpr int NSTAGE = 3;
 constexpr int THREADS = 192;
-constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+constexpr int REC_BYTES = 2 * TN * 16;  // two tiles of per-row leaf records (LEAF / FILTER epilogues)
+constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */ + REC_BYTES;
 static_assert(SD * 2 * 4 == ROWB, "a slab row is 8 x^2 features + 8 x features");
 static_assert(TQ == 2 * TM, "two accumulators per CTA tile");
 
@@ -197,6 +198,7 @@ tc_score_kernel(const unsigned char *__restrict__ A, const unsigned char *__rest
     const uint32_t full0 = bars, empty0 = bars + 8 * NSTAGE, accf = bars + 16 * NSTAGE, acce = accf + 8;
     const uint32_t tmem_slot = acce + 8;
     uint32_t *tmem_slot_ptr = reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+    float4 *recs_s = reinterpret_cast<float4 *>(smem_raw + (bars + 256 - smem_u32(smem_raw)));  // [2][TN]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -279,12 +281,23 @@ tc_score_kernel(const unsigned char *__restrict__ A, const unsigned char *__rest
         // ===== epilogue: warp w reads TMEM lanes 32*(w%4) .. +31 (lane = query of the 128-query half)
         const int quarter = warp & 3;
         uint32_t aphase = 0;
+        int rbuf = 0;
         for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
             int nt, qt;
             tile_coords(t, n_qtiles, n_ntiles, pq, nt, qt);
+            const long long n0 = (long long)(nt_begin + nt) * TN;
+            const float4 *recs = recs_s + rbuf * TN;
+            if (MODE != EPI_NODE) {
+                // the tile's leaf records go to shared memory while the MMAs of the tile are still running; two
+                // buffers, so that one named barrier per tile also protects the buffer of the tile before
+                const int e = threadIdx.x - 64;  // 0..127 over the four epilogue warps
+                recs_s[rbuf * TN + e] = __ldg(epi.leaf_rec + n0 + e);
+                recs_s[rbuf * TN + 128 + e] = __ldg(epi.leaf_rec + n0 + 128 + e);
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                rbuf ^= 1;
+            }
             mbar_wait(accf, aphase);
             tc_fence_after();
-            const long long n0 = (long long)(nt_begin + nt) * TN;
             const long long ldq = epi.ldq;
 #pragma unroll 1
             for (int qh = 0; qh < 2; qh++) {
@@ -303,24 +316,38 @@ tc_score_kernel(const unsigned char *__restrict__ A, const unsigned char *__rest
                     uint32_t v[32];
                     CW_TMEM_LD32(taddr + (uint32_t)(c * 32), v);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (MODE == EPI_NODE) {
 #pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        const long long n = n0 + c * 32 + j;
-                        if (MODE == EPI_NODE) {
+                        for (int j = 0; j < 32; j++) {
+                            const long long n = n0 + c * 32 + j;
                             epi.out[n * ldq + q] = fmaf(-0.5f, __uint_as_float(v[j]), __ldg(epi.hconst + n));
-                        } else {
-                            const float4 r = __ldg(epi.leaf_rec + n);  // uniform: one broadcast load per row
+                        }
+                    } else {
+                        // all loads of the 32 rows first (record: one broadcast load per row; ancestor sum: one
+                        // coalesced line per row), then the stores / appends: a store between them would keep the
+                        // compiler from overlapping the dependent load pairs
+                        float sc[32];
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            const float4 r = recs[c * 32 + j];  // broadcast read
                             const int par = __float_as_int(r.w);
                             const float s = fmaf(-0.5f, __uint_as_float(v[j]), r.x);
                             const float cp = par >= 0 ? __ldg(epi.C + (long long)par * ldq + q) : 0.0f;
-                            const float score = fmaf(r.y, s, cp) * r.z;
-                            if (MODE == EPI_LEAF) {
-                                epi.out[n * ldq + q] = score;
-                            } else if (live && n < epi.n_rows && score >= tau) {
-                                const int at = atomicAdd(epi.cnt + q, 1);
-                                if (at < epi.cap) {
-                                    epi.cand_val[q * epi.cap + at] = score;
-                                    epi.cand_row[q * epi.cap + at] = (int)n;
+                            sc[j] = fmaf(r.y, s, cp) * r.z;
+                        }
+                        if (MODE == EPI_LEAF) {
+#pragma unroll
+                            for (int j = 0; j < 32; j++) epi.out[(n0 + c * 32 + j) * ldq + q] = sc[j];
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; j++) {
+                                const long long n = n0 + c * 32 + j;
+                                if (live && n < epi.n_rows && sc[j] >= tau) {
+                                    const int at = atomicAdd(epi.cnt + q, 1);
+                                    if (at < epi.cap) {
+                                        epi.cand_val[q * epi.cap + at] = sc[j];
+                                        epi.cand_row[q * epi.cap + at] = (int)n;
+                                    }
                                 }
                             }
                         }
