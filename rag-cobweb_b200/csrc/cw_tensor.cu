@@ -50,11 +50,13 @@ constexpr int A_BYTES = 2 * A_IMG;   // hi + lo
 constexpr int B_BYTES = 2 * B_IMG;
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;  // 64 KB
 constexpr int NSTAGE = 3;
-constexpr int THREADS = 192;
+constexpr int THREADS = 320;      // producer warp, MMA warp, eight epilogue warps (two per TMEM lane quarter)
+constexpr int EPI_THREADS = THREADS - 64;
 constexpr int REC_BYTES = 2 * TN * 16;  // two tiles of per-row leaf records (LEAF / FILTER epilogues)
 constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */ + REC_BYTES;
 static_assert(SD * 2 * 4 == ROWB, "a slab row is 8 x^2 features + 8 x features");
 static_assert(TQ == 2 * TM, "two accumulators per CTA tile");
+static_assert(THREADS - 64 == TN, "one leaf record per epilogue thread");
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -207,7 +209,7 @@ tc_score_kernel(const unsigned char *__restrict__ A, const unsigned char *__rest
             mbar_init(empty0 + 8 * s, 1);
         }
         mbar_init(accf, 1);
-        mbar_init(acce, 4);  // one arrival per epilogue warp
+        mbar_init(acce, EPI_THREADS / 32);  // one arrival per epilogue warp
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {  // TMEM: all 512 columns (two 128 x 256 fp32 accumulators); this warp also frees them
@@ -278,8 +280,9 @@ tc_score_kernel(const unsigned char *__restrict__ A, const unsigned char *__rest
         }
         __syncwarp();
     } else {
-        // ===== epilogue: warp w reads TMEM lanes 32*(w%4) .. +31 (lane = query of the 128-query half)
-        const int quarter = warp & 3;
+        // ===== epilogue: warp w reads TMEM lanes 32*(w%4) .. +31 (lane = query of the 128-query half); the two
+        // warps of a quarter take alternate 32-column batches
+        const int quarter = warp & 3, sub = (warp - 2) >> 2;
         uint32_t aphase = 0;
         int rbuf = 0;
         for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
@@ -290,10 +293,9 @@ tc_score_kernel(const unsigned char *__restrict__ A, const unsigned char *__rest
             if (MODE != EPI_NODE) {
                 // the tile's leaf records go to shared memory while the MMAs of the tile are still running; two
                 // buffers, so that one named barrier per tile also protects the buffer of the tile before
-                const int e = threadIdx.x - 64;  // 0..127 over the four epilogue warps
+                const int e = threadIdx.x - 64;  // 0..255 over the eight epilogue warps
                 recs_s[rbuf * TN + e] = __ldg(epi.leaf_rec + n0 + e);
-                recs_s[rbuf * TN + 128 + e] = __ldg(epi.leaf_rec + n0 + 128 + e);
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
                 rbuf ^= 1;
             }
             mbar_wait(accf, aphase);
@@ -312,7 +314,7 @@ tc_score_kernel(const unsigned char *__restrict__ A, const unsigned char *__rest
                     if (live) tau = epi.tau[q];
                 }
 #pragma unroll 1
-                for (int c = 0; c < TN / 32; c++) {
+                for (int c = sub; c < TN / 32; c += 2) {
                     uint32_t v[32];
                     CW_TMEM_LD32(taddr + (uint32_t)(c * 32), v);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
