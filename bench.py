@@ -221,6 +221,10 @@ def _run_engine(args, wl):
     # kernels per chunk: tensor mode = query operands, tcgen05 scores, paths/top-kc, merge, re-score;
     # FP32 mode = query tiles, FFMA scores, paths/top-k, merge
     launches_per_step = (5 if tensor else 4) * chunks
+    if tensor and args.mode == "tf32x3f" and getattr(ix, "fx", None):
+        # query operands, internal scores, one cumulative-sum launch per level, sample scores, sample paths + merge,
+        # filter scores, select, re-score
+        launches_per_step = (8 + len(ix.fx["F"]["level_off"]) - 1) * chunks
 
     store_mode = args.shard == "store" and world > 1
     if store_mode:
@@ -284,7 +288,7 @@ def _run_engine(args, wl):
         ids_f, vals_f, _ = ix.predict(q_dev, k)
         ms_dev32 = timed(lambda: ix.predict(q_dev, k), 3) / 3
         ms_k32 = timed(lambda: ix.node_scores(q_dev[:nq_k]), 3) / 3
-        ix.set_mode("tf32x3")
+        ix.set_mode(args.mode)
         fp32 = {"queries_per_s": qn / (ms_dev32 * 1e-3), "ms_per_step": ms_dev32, "score_kernel_ms": ms_k32,
                 "ids_identical": bool(torch.equal(ids_t, ids_f)), "scores_bit_identical": bool(torch.equal(vals_t, vals_f))}
 
@@ -344,7 +348,7 @@ def _run_engine(args, wl):
         if tensor:
             w.set_dense_mode("fp32")
             single["fp32"] = single_query_ms()
-            w.set_dense_mode("tf32x3")
+            w.set_dense_mode(args.mode)
 
     # correctness inside the bench: recall@k of the timed configuration (target among returned ids)
     ids, _ = step_device()
@@ -443,11 +447,14 @@ def _run_engine(args, wl):
                    "parallelism": (f"store sharded x{world} (sentences + ancestor nodes), NCCL all-gather + top-k merge"
                                    if store_mode else f"replicated store, query-sharded x{world}") if world > 1 else "single GPU",
                    "l2": "inputs exceed L2 (node matrices %.0f MB per pass)" % (8.0 * nn * dim / 1e6),
-                   "scoring": ("tf32x3: tcgen05 split-TF32 pre-filter (top-%d candidates) + exact FP32 re-score; ids and scores "
-                               "bit-identical to the FP32-pipe path" % ix.candidates(k)) if tensor else "fp32: FP32-pipe FFMA2 kernel"},
+                   "scoring": ("%s: tcgen05 split-TF32 pre-filter%s (top-%d candidates) + exact FP32 re-score; ids and scores "
+                               "bit-identical to the FP32-pipe path" % (args.mode, " with fused path sums / candidate filter"
+                                                                        if args.mode == "tf32x3f" else "", ix.candidates(k)))
+                   if tensor else "fp32: FP32-pipe FFMA2 kernel"},
         "e2e": {"value": total_q * args.steps / (ms_host * 1e-3), "unit": "queries/s",
                 "h2d_bytes_per_step": int(qn * dim * 4), "d2h_bytes_per_step": int(qn * k * 8),
-                "api": "cw_predict_dense_host (C ABI, pinned host buffers)"},
+                "api": ("DenseIndex.predict_host (pinned host buffers; fused pipeline of C-ABI calls)" if args.mode == "tf32x3f"
+                        else "cw_predict_dense_host (C ABI, pinned host buffers)")},
         "gpu_launches": launches_per_step * args.steps,
         "roofline": roofline,
         "cpu_baseline": cpu,
@@ -483,9 +490,10 @@ def main():
     ap.add_argument("--docs", type=int)
     ap.add_argument("--queries", type=int)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--mode", default="tf32x3", choices=["tf32x3", "tf32x3f", "fp32"],
-                    help="node scores on the tensor cores (tcgen05 split-TF32 pre-filter + exact FP32 re-score, default) "
-                         "or on the FP32 pipe; the results are identical")
+    ap.add_argument("--mode", default="tf32x3f", choices=["tf32x3f", "tf32x3", "fp32"],
+                    help="tf32x3f (default): tcgen05 split-TF32 pre-filter with the path sums and the candidate filter fused "
+                         "into the score kernel's epilogue + exact FP32 re-score; tf32x3: the same pre-filter through the "
+                         "score matrix and the path kernel; fp32: everything on the FP32 pipe.  The results are identical")
     ap.add_argument("--shard", default="query", choices=["query", "store"],
                     help="N>1: 'query' replicates the store and shards the batch (weak scaling, default); "
                          "'store' shards sentences+nodes, every rank answers the whole batch, per-rank top-k "

@@ -372,6 +372,14 @@ def test_store_sharded_predict_matches_full():
         cv = torch.cat([p[1] for p in parts], 1)
         mi, mv = parallel.merge_topk(ci, cv, k)
         assert torch.equal(mi, full_i) and torch.equal(mv, full_v)
+    # the same through the tensor-core modes (a shard index carries global sentence ids and its own row subset)
+    for mode in ("tf32x3", "tf32x3f"):
+        w.set_dense_mode(mode)
+        w._shard_key = None
+        parts = [w.predict_fast_sharded(q, k, world=2, rank=r) for r in range(2)]
+        mi, mv = parallel.merge_topk(torch.cat([p[0] for p in parts], 1), torch.cat([p[1] for p in parts], 1), k)
+        assert torch.equal(mi, full_i) and torch.equal(mv, full_v), mode
+    w.set_dense_mode("fp32")
 
 
 def test_whitening_transform_matches_reference(golden_dir, tmp_path):
