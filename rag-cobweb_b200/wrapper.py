@@ -37,6 +37,7 @@ class DenseIndex:
     # [nodes, queries] score matrix and the path kernel disappear for the leaves; same exact re-score, same results
     MODES = ("fp32", "tf32x3", "tf32x3f")
     FUSED_CAP = 1024  # candidate slots per query of the filtering epilogue
+    FUSED_MIN_QUERIES = 256
     EPS_SCALE = 2.0 ** -18  # bound of |tf32x3 - fp32| leaf score relative to the operand magnitudes (cw_dense_rescore)
 
     def __init__(self, tree, leaf_of_sentence, level_weights=None, sentence_ids=None):
@@ -350,7 +351,9 @@ class DenseIndex:
         kc = self.candidates(k, _level) if (tensor and not want_leaf_scores) else 0
         if tensor and kc == 0 and k > 0 and not want_leaf_scores:
             return self.predict(Q, k, mode="fp32")  # this k / depth is not served by the re-score kernel
-        fused = mode == "tf32x3f" and kc > 0 and _level == 0 and getattr(self, "fx", None) is not None
+        # small batches: the fused pipeline's extra launches (one per tree level) cost more than the path kernel saves
+        fused = (mode == "tf32x3f" and kc > 0 and _level == 0 and getattr(self, "fx", None) is not None and
+                 Q.shape[0] >= self.FUSED_MIN_QUERIES)
         nq_total = Q.shape[0]
         step = self.chunk_queries()
         sids = torch.empty((nq_total, max(k, 1)), dtype=torch.int32, device=Q.device)

@@ -612,3 +612,6 @@ def test_fused_tensor_predict_matches_fp32_path(n, d, kind, k, weights):
     assert ix.n_fallback - n0 <= 8
     w.set_dense_mode("tf32x3f")
     assert w.cobweb_predict_fast(q[5], k=k, return_ids=True, is_embedding=True) == list(ids32[5].cpu().numpy())
+    ix.FUSED_MIN_QUERIES = 1  # the fused pipeline itself on a tiny batch
+    a, b, _ = ix.predict(qd[:3], k)
+    assert torch.equal(a, ids32[:3]) and torch.equal(b, v32[:3])
