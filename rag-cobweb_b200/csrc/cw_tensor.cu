@@ -298,59 +298,82 @@ tc_score_kernel(const unsigned char *__restrict__ A, const unsigned char *__rest
                 asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
                 rbuf ^= 1;
             }
-            mbar_wait(accf, aphase);
-            tc_fence_after();
             const long long ldq = epi.ldq;
+            if (MODE == EPI_NODE) {
+                mbar_wait(accf, aphase);
+                tc_fence_after();
 #pragma unroll 1
-            for (int qh = 0; qh < 2; qh++) {
-                const long long q0 = (long long)qt * TQ + qh * TM;
-                if (q0 >= ldq) break;  // a half-tile of pure padding past the score matrix
-                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(qh * TN);
-                const long long q = q0 + quarter * 32 + lane;
-                float tau = 0.0f;
-                bool live = false;
-                if (MODE == EPI_FILTER) {
-                    live = q < epi.nq;
-                    if (live) tau = epi.tau[q];
-                }
+                for (int qh = 0; qh < 2; qh++) {
+                    const long long q0 = (long long)qt * TQ + qh * TM;
+                    if (q0 >= ldq) break;  // a half-tile of pure padding past the score matrix
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(qh * TN);
+                    const long long q = q0 + quarter * 32 + lane;
 #pragma unroll 1
-                for (int c = sub; c < TN / 32; c += 2) {
-                    uint32_t v[32];
-                    CW_TMEM_LD32(taddr + (uint32_t)(c * 32), v);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (MODE == EPI_NODE) {
+                    for (int c = sub; c < TN / 32; c += 2) {
+                        uint32_t v[32];
+                        CW_TMEM_LD32(taddr + (uint32_t)(c * 32), v);
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                         for (int j = 0; j < 32; j++) {
                             const long long n = n0 + c * 32 + j;
                             epi.out[n * ldq + q] = fmaf(-0.5f, __uint_as_float(v[j]), __ldg(epi.hconst + n));
                         }
-                    } else {
-                        // all loads of the 32 rows first (record: one broadcast load per row; ancestor sum: one
-                        // coalesced line per row), then the stores / appends: a store between them would keep the
-                        // compiler from overlapping the dependent load pairs
-                        float sc[32];
+                    }
+                }
+            } else {
+                // This warp's eight batches of 32 rows: b -> (query half b / 4, column block sub + 2 (b % 4)).  The
+                // ancestor sums C[parent][q] of a batch do not depend on the accumulator, so they are fetched one
+                // batch ahead -- the first batch while the MMAs of the tile are still running.
+                const long long qbase = (long long)qt * TQ + quarter * 32 + lane;
+                auto fetch_cp = [&](int b, float (&cp)[32]) {
+                    const int qh = b >> 2, c = sub + 2 * (b & 3);
+                    const bool qok = (long long)qt * TQ + qh * TM < ldq;
+                    const float *Cq = epi.C + qbase + qh * TM;
 #pragma unroll
-                        for (int j = 0; j < 32; j++) {
-                            const float4 r = recs[c * 32 + j];  // broadcast read
-                            const int par = __float_as_int(r.w);
-                            const float s = fmaf(-0.5f, __uint_as_float(v[j]), r.x);
-                            const float cp = par >= 0 ? __ldg(epi.C + (long long)par * ldq + q) : 0.0f;
-                            sc[j] = fmaf(r.y, s, cp) * r.z;
-                        }
+                    for (int j = 0; j < 32; j++) {
+                        const int par = __float_as_int(recs[c * 32 + j].w);  // broadcast read
+                        cp[j] = (qok && par >= 0) ? __ldg(Cq + (long long)par * ldq) : 0.0f;
+                    }
+                };
+                float tau0 = 0.0f, tau1 = 0.0f;
+                bool live0 = false, live1 = false;
+                if (MODE == EPI_FILTER) {
+                    live0 = qbase < epi.nq;
+                    live1 = qbase + TM < epi.nq;
+                    if (live0) tau0 = epi.tau[qbase];
+                    if (live1) tau1 = epi.tau[qbase + TM];
+                }
+                float cpn[32];
+                fetch_cp(0, cpn);
+                mbar_wait(accf, aphase);
+                tc_fence_after();
+#pragma unroll 1
+                for (int b = 0; b < 8; b++) {
+                    const int qh = b >> 2, c = sub + 2 * (b & 3);
+                    if ((long long)qt * TQ + qh * TM >= ldq) break;  // a half-tile of pure padding past the score matrix
+                    const long long q = qbase + qh * TM;
+                    uint32_t v[32];
+                    CW_TMEM_LD32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(qh * TN + c * 32), v);
+                    float cp[32];
+#pragma unroll
+                    for (int j = 0; j < 32; j++) cp[j] = cpn[j];
+                    if (b + 1 < 8) fetch_cp(b + 1, cpn);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    const float tau = qh ? tau1 : tau0;
+                    const bool live = qh ? live1 : live0;
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        const float4 r = recs[c * 32 + j];  // broadcast read
+                        const float s = fmaf(-0.5f, __uint_as_float(v[j]), r.x);
+                        const float score = fmaf(r.y, s, cp[j]) * r.z;
+                        const long long n = n0 + c * 32 + j;
                         if (MODE == EPI_LEAF) {
-#pragma unroll
-                            for (int j = 0; j < 32; j++) epi.out[(n0 + c * 32 + j) * ldq + q] = sc[j];
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; j++) {
-                                const long long n = n0 + c * 32 + j;
-                                if (live && n < epi.n_rows && sc[j] >= tau) {
-                                    const int at = atomicAdd(epi.cnt + q, 1);
-                                    if (at < epi.cap) {
-                                        epi.cand_val[q * epi.cap + at] = sc[j];
-                                        epi.cand_row[q * epi.cap + at] = (int)n;
-                                    }
-                                }
+                            epi.out[n * ldq + q] = score;
+                        } else if (live && n < epi.n_rows && score >= tau) {
+                            const int at = atomicAdd(epi.cnt + q, 1);
+                            if (at < epi.cap) {
+                                epi.cand_val[q * epi.cap + at] = score;
+                                epi.cand_row[q * epi.cap + at] = (int)n;
                             }
                         }
                     }
