@@ -615,3 +615,8 @@ def test_fused_tensor_predict_matches_fp32_path(n, d, kind, k, weights):
     ix.FUSED_MIN_QUERIES = 1  # the fused pipeline itself on a tiny batch
     a, b, _ = ix.predict(qd[:3], k)
     assert torch.equal(a, ids32[:3]) and torch.equal(b, v32[:3])
+    # candidate-buffer overflow: with 8 slots per query nearly every query overflows, is flagged by cw_tc_select and
+    # answered by the unfused path -- same result
+    ix.FUSED_CAP, ix._ws, e0 = 8, None, ix.n_escalated
+    a, b, _ = ix.predict(qd, k)
+    assert torch.equal(a, ids32) and torch.equal(b, v32) and ix.n_escalated - e0 > 100
