@@ -620,3 +620,27 @@ def test_fused_tensor_predict_matches_fp32_path(n, d, kind, k, weights):
     ix.FUSED_CAP, ix._ws, e0 = 8, None, ix.n_escalated
     a, b, _ = ix.predict(qd, k)
     assert torch.equal(a, ids32) and torch.equal(b, v32) and ix.n_escalated - e0 > 100
+
+
+def test_tensor_modes_small_and_odd_shapes():
+    """Both tensor modes against the FP32 path on shapes around the tile edges: tiny trees, attribute counts that are
+    not multiples of the 8-attribute slab, k = 1, acuity cutoff, a custom prior variance, one-query batches."""
+    cases = [(40, 7, "whitened", 1, {}), (257, 33, "unit", 4, {}), (2500, 200, "unit", 4, dict(acuity_cutoff=True)),
+             (900, 9, "whitened", 3, dict(prior_var=0.01)), (3000, 17, "unit", 10, {})]
+    for n, d, kind, k, kw in cases:
+        x = synth.corpus(n, d, kind, seed=21)
+        w = CobwebWrapper(corpus=[None], corpus_embeddings=x[:1])
+        w.tree, w.sentences, w._leaf_of_sentence = CobwebTorchTree((d,), **kw), [], np.zeros(0, np.int32)  # tree with these flags
+        w.add_sentences([None] * n, x)
+        q, _ = synth.queries(x, 70, kind, seed=22)
+        qd = torch.from_numpy(q).cuda()
+        w.build_prediction_index()
+        ix = w._index
+        ids32, v32, _ = ix.predict(qd, k)
+        for mode in ("tf32x3", "tf32x3f"):
+            ix.set_mode(mode)
+            ix.FUSED_MIN_QUERIES = 1
+            for batch in (qd, qd[:1]):
+                a, b, _ = ix.predict(batch, k)
+                assert torch.equal(a, ids32[: len(batch)]) and torch.equal(b, v32[: len(batch)]), (n, d, kind, k, mode, len(batch))
+        ix.set_mode("fp32")
