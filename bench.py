@@ -425,6 +425,9 @@ def _run_engine(args, wl):
                     "executed_tflops": 3.0 * achieved, "executed_frac": 3.0 * achieved / peak,
                     "executed_note": "every product is hi*hi + hi*lo + lo*hi of split-TF32 operands: 3 tcgen05.mma per algorithmic "
                                      "MMA, so frac <= 1/3 by construction; executed_frac is the tensor-pipe utilisation",
+                    "kernel_note": ("timed alone over ALL index rows with the node-score epilogue; a fused step runs the same kernel "
+                                    "three times (internal rows / sampled leaf tiles / filtered leaf tiles), together once over "
+                                    "every row") if args.mode == "tf32x3f" else None,
                     "tf32_cublas_tflops": tf32_peak,
                     "tensor_pipe_tflops_at_clock": 148 * 4096 * (clocks["sm_mhz"] or 0) * 1e6 / 1e12 if clocks else None,
                     "pipe_note": "tensor_pipe_tflops_at_clock = 148 SMs x 2048 TF32 FMA/clk x the SM clock sampled under load: the "
