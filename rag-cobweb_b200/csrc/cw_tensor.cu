@@ -361,19 +361,33 @@ tc_score_kernel(const unsigned char *__restrict__ A, const unsigned char *__rest
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                     const float tau = qh ? tau1 : tau0;
                     const bool live = qh ? live1 : live0;
+                    float sc[32];
+                    unsigned hit = 0;
 #pragma unroll
                     for (int j = 0; j < 32; j++) {
                         const float4 r = recs[c * 32 + j];  // broadcast read
                         const float s = fmaf(-0.5f, __uint_as_float(v[j]), r.x);
-                        const float score = fmaf(r.y, s, cp[j]) * r.z;
-                        const long long n = n0 + c * 32 + j;
-                        if (MODE == EPI_LEAF) {
-                            epi.out[n * ldq + q] = score;
-                        } else if (live && n < epi.n_rows && score >= tau) {
-                            const int at = atomicAdd(epi.cnt + q, 1);
-                            if (at < epi.cap) {
-                                epi.cand_val[q * epi.cap + at] = score;
-                                epi.cand_row[q * epi.cap + at] = (int)n;
+                        sc[j] = fmaf(r.y, s, cp[j]) * r.z;
+                        if (MODE == EPI_LEAF) epi.out[(n0 + c * 32 + j) * ldq + q] = sc[j];
+                        else if (sc[j] >= tau) hit |= 1u << j;
+                    }
+                    if (MODE == EPI_FILTER) {
+                        // rows past the index are tile padding (only in the last tile)
+                        const long long left = (long long)epi.n_rows - (n0 + c * 32);
+                        if (left < 32) hit &= left <= 0 ? 0u : (1u << left) - 1u;
+                        if (live && hit) {
+                            // one counter update per thread and batch: a returning atomic per hit would put an L2
+                            // round trip between the rows
+                            int at = atomicAdd(epi.cnt + q, __popc(hit));
+#pragma unroll
+                            for (int j = 0; j < 32; j++) {
+                                if (hit >> j & 1) {
+                                    if (at < epi.cap) {
+                                        epi.cand_val[q * epi.cap + at] = sc[j];
+                                        epi.cand_row[q * epi.cap + at] = (int)(n0 + c * 32 + j);
+                                    }
+                                    at++;
+                                }
                             }
                         }
                     }
