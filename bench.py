@@ -350,6 +350,27 @@ def _run_engine(args, wl):
             single["fp32"] = single_query_ms()
             w.set_dense_mode(args.mode)
 
+    # context: the reference's brute-force inner-product baseline (retrieve_torch_dot, its stand-in for FAISS
+    # IndexFlatIP) on the same corpus and queries -- library GEMM + top-k, batched on the GPU and, on rank 0 at N = 1,
+    # on the host cores for a bounded sample
+    from rag_cobweb_b200.evaluate import retrieve_dot_batch
+    x_dev = torch.from_numpy(x).cuda()
+    retrieve_dot_batch(x_dev, q_dev, k)
+    ms_dot = timed(lambda: retrieve_dot_batch(x_dev, q_dev, k), 3) / 3
+    dot_ids = retrieve_dot_batch(x_dev, q_dev, k).cpu().numpy()
+    brute = {"gpu_queries_per_s": qn / (ms_dot * 1e-3),
+             "recall_at_k": float(np.mean([t in g for t, g in zip(targets_all[lo:hi], dot_ids)])),
+             "note": "torch.matmul + torch.topk over the raw embeddings (retrieve_torch_dot semantics); a different retrieval "
+                     "function than Cobweb's path-averaged log-likelihood, listed for context only"}
+    del x_dev
+    if world == 1 and not args.no_cpu_baseline:
+        xs, qs = torch.from_numpy(x), torch.from_numpy(q_all[:512])
+        torch.topk(qs @ xs.T, k, dim=1)
+        t0 = time.time()
+        torch.topk(qs @ xs.T, k, dim=1)
+        brute["cpu_queries_per_s"] = 512 / (time.time() - t0)
+        brute["cpu_sample"] = f"512 queries, torch CPU matmul + topk, {torch.get_num_threads()} threads"
+
     # correctness inside the bench: recall@k of the timed configuration (target among returned ids)
     ids, _ = step_device()
     got = ids.cpu().numpy()[lo:hi] if (world > 1 and not store_mode) else ids.cpu().numpy()
@@ -464,6 +485,7 @@ def _run_engine(args, wl):
         "clocks": clocks,
         "recall_at_k": recall,
         "fp32_path": fp32,
+        "brute_force_ip": brute,
         "single_query_ms": single,
         "index_build_s": index_build_s,
         "index_bytes": ix.bytes(),

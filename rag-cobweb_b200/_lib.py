@@ -22,7 +22,7 @@ IFIT_NODE_SLACK, IFIT_POOL_SLACK = 160, 16384
 EXPORTS = ["cw_version", "cw_last_error", "cw_store_init", "cw_ifit", "cw_set_ifit_cluster", "cw_categorize_ctas", "cw_categorize",
            "cw_index_build", "cw_xt_floats", "cw_score_ldq", "cw_dense_node_scores", "cw_topk_chunks", "cw_dense_paths_topk",
            "cw_predict_dense_host", "cw_tc_b_bytes", "cw_tc_a_bytes", "cw_tc_index_build",
-           "cw_dense_node_scores_tc", "cw_tc_build_queries", "cw_tc_score_tiles", "cw_tc_cumsum_level", "cw_tc_select",
+           "cw_dense_node_scores_tc", "cw_tc_build_queries", "cw_tc_score_tiles", "cw_tc_cumsum_level", "cw_tc_select", "cw_dense_rows_topk",
            "cw_rescore_smem_bytes", "cw_rescore_rows_build", "cw_dense_rescore", "cw_rank_scores_bwd", "cw_whiten", "cw_ffma_peak", "cw_ffma2_peak"]
 
 
@@ -95,6 +95,7 @@ def load():
                                     C.c_int32, vp, vp, vp, vp]
     L.cw_tc_cumsum_level.argtypes = [vp, i64, C.c_int32, C.c_int32, vp, vp, vp]
     L.cw_tc_select.argtypes = [i64, i32, vp, vp, C.c_int32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.cw_dense_rows_topk.argtypes = [vp, i64, i64, C.c_int32, vp, vp, i32, vp, vp, vp, vp]
     L.cw_rescore_smem_bytes.restype = i64
     L.cw_rescore_smem_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32]
     L.cw_rescore_rows_build.argtypes = [C.POINTER(CwStore), vp, C.c_int32, vp, vp]

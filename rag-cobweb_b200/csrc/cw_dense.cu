@@ -495,6 +495,108 @@ paths_topk_kernel(const float *__restrict__ ST, unsigned ldq, long long nq, int 
     }
 }
 
+// ------------------------------------------------------------------ top-k over the rows of a leaf-score matrix
+// Used by the fused tensor mode for its sample of the leaves: S[row * ldq + q] already is the leaf score, a row's
+// sentences are sent_ids[sent_off[row] .. sent_off[row + 1]).  Same list handling as the path kernel (per-lane
+// sorted k-lists in shared memory behind a register threshold, k <= 32, per-chunk lists merged afterwards, k-th-best
+// bound shared between the chunks) without any path bookkeeping: eight independent row loads in flight per warp.
+// Pre-pass of rows_topk_kernel: the rows are cut into k contiguous segments; the smallest of the k segment maxima
+// is a lower bound of the k-th best score (k different rows reach it), so it can seed the threshold the chunks
+// share and spare every chunk the k ln(n/k) insertions of a cold list.  grid (k segments, query-group blocks).
+__global__ void __launch_bounds__(256)
+rows_segmax_kernel(const float *__restrict__ S, unsigned ldq, long long nq, int n_rows, int seg_len, int *shared_thr) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const long long g = (long long)blockIdx.y * wpb + warp;
+    if (g * 32 >= nq) return;
+    const long long q = g * 32 + lane;
+    const bool qvalid = q < nq;
+    const float *col = S + (qvalid ? q : g * 32);
+    const int r0 = blockIdx.x * seg_len, r1 = min(n_rows, r0 + seg_len);
+    float m[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) m[i] = -__int_as_float(0x7f800000);
+    for (int rb = r0; rb < r1; rb += 8) {
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            if (rb + i < r1) m[i] = fmaxf(m[i], col[(size_t)(unsigned)(rb + i) * ldq]);
+    }
+    float mx = fmaxf(fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])), fmaxf(fmaxf(m[4], m[5]), fmaxf(m[6], m[7])));
+    if (qvalid && r1 > r0) atomicMin(shared_thr + q, float_key(mx));
+}
+
+__global__ void __launch_bounds__(256)
+rows_topk_kernel(const float *__restrict__ S, unsigned ldq, long long nq, int n_rows, const int *__restrict__ sent_off,
+                 const int *__restrict__ sent_ids, int k, float *cand_s, int *cand_i, int n_chunks, int chunk_len,
+                 int *shared_thr) {
+    extern __shared__ __align__(16) unsigned char rt_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    float *Ls = reinterpret_cast<float *>(rt_smem) + (size_t)warp * k * 32;
+    int *Li = reinterpret_cast<int *>(reinterpret_cast<float *>(rt_smem) + (size_t)wpb * k * 32) + (size_t)warp * k * 32;
+    const float NEG_INF = -__int_as_float(0x7f800000);
+    for (int i = lane; i < 32 * k; i += 32) { Ls[i] = NEG_INF; Li[i] = -1; }
+    __syncwarp();
+    const long long g = (long long)blockIdx.y * wpb + warp;
+    if (g * 32 >= nq) return;
+    const long long q = g * 32 + lane;
+    const bool qvalid = q < nq;
+    const float *col = S + (qvalid ? q : g * 32);
+    const int chunk = blockIdx.x;
+    const int r0 = chunk * chunk_len, r1 = min(n_rows, r0 + chunk_len);
+    float thr_s = NEG_INF, gthr = NEG_INF, published = NEG_INF;
+    int thr_i = 0x7fffffff;
+    int *gslot = shared_thr + (qvalid ? q : 0);
+    for (int rb = r0; rb < r1; rb += 8) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = rb + i < r1 ? col[(size_t)(unsigned)(rb + i) * ldq] : NEG_INF;
+        if (qvalid) {
+            if (thr_i != 0x7fffffff && thr_s > published) {
+                published = thr_s;
+                atomicMax(gslot, float_key(thr_s));
+            }
+            gthr = fmaxf(gthr, key_float(__ldcg(gslot)));
+        }
+#pragma unroll 1
+        for (int i = 0; i < 8; i++) {
+            const int row = rb + i;
+            if (row >= r1) break;
+            const float acc = v[i];
+            const int s0 = sent_off[row], s1 = sent_off[row + 1];
+            for (int s = s0; s < s1; s++) {
+                const int sid = sent_ids[s];
+                unsigned need = __ballot_sync(0xffffffffu, qvalid && acc >= gthr &&
+                                                               (acc > thr_s || (acc == thr_s && (unsigned)sid < (unsigned)thr_i)));
+                while (need) {  // one rank per lane: read, ballot the insertion point, shift by one, done
+                    const int L = __ffs(need) - 1;
+                    need &= need - 1;
+                    const float cv = __shfl_sync(0xffffffffu, acc, L);
+                    const int base = L * k;
+                    float es = NEG_INF;
+                    int ei = -1;
+                    if (lane < k) { es = Ls[base + lane]; ei = Li[base + lane]; }
+                    const int pos = __popc(__ballot_sync(0xffffffffu, es > cv || (es == cv && ei < sid)));
+                    const float ps = __shfl_sync(0xffffffffu, es, (k - 2) & 31);
+                    const int pi = __shfl_sync(0xffffffffu, ei, (k - 2) & 31);
+                    if (lane >= pos && lane + 1 < k) { Ls[base + lane + 1] = es; Li[base + lane + 1] = ei; }
+                    if (lane == pos) { Ls[base + lane] = cv; Li[base + lane] = sid; }
+                    if (lane == L) {
+                        const bool cand_last = (k < 2) || (pos == k - 1);
+                        thr_s = cand_last ? cv : ps;
+                        thr_i = cand_last ? sid : pi;
+                        if (thr_i < 0) thr_i = 0x7fffffff;
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    }
+    if (qvalid) {
+        float *os = cand_s + (q * n_chunks + chunk) * k;
+        int *oi = cand_i + (q * n_chunks + chunk) * k;
+        for (int r = 0; r < k; r++) { os[r] = Ls[lane * k + r]; oi[r] = Li[lane * k + r]; }
+    }
+}
+
 // Running top-k of one warp, kept sorted across the lanes: rank r lives in lane r%32, slot r/32
 // (register arrays ls/li, fully unrolled).  Used to merge the per-chunk candidate lists.
 __device__ __forceinline__ void topk_init(float (&ls)[PT_SLOTS], int (&li)[PT_SLOTS]) {
@@ -793,4 +895,56 @@ extern "C" int cw_predict_dense_host(const cw_index *ix, const cw_tc_index *tx, 
     }
     delete[] list;
     return rc;
+}
+
+extern "C" int cw_dense_rows_topk(const float *scores, int64_t ldq, int64_t nq, int32_t n_rows, const int32_t *sent_off,
+                                  const int32_t *sent_ids, int k, int32_t *out_sid, float *out_score, int32_t *scratch,
+                                  void *stream) {
+    if (!scores || !sent_off || !sent_ids || !out_sid || !out_score || !scratch || nq < 0 || n_rows < 1 || k < 1 || k > 32 ||
+        ldq < cw_score_ldq(nq) || ldq > 0x7fffffffLL) {
+        cw_set_error("cw_dense_rows_topk: bad argument (k=%d, 1..32)", k);
+        return CW_E_ARG;
+    }
+    if (nq == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int wpb = 8;
+    const size_t smem = (size_t)wpb * k * 256;
+    int ctas = (int)((227 * 1024) / (smem + 1024));
+    if (ctas > 8) ctas = 8;
+    const long long groups = (nq + 31) / 32, gblocks = (groups + wpb - 1) / wpb;
+    long long want = (long long)sms * ctas / gblocks;
+    const long long max_chunks = cw_topk_chunks(n_rows) - 1;
+    if (want > max_chunks) want = max_chunks;
+    if (want < 1) want = 1;
+    const int chunk_len = (int)((n_rows + want - 1) / want);
+    const int n_chunks = (n_rows + chunk_len - 1) / chunk_len;
+    float *cand_s = reinterpret_cast<float *>(scratch);
+    int *cand_i = scratch + (size_t)nq * n_chunks * k;
+    int *shared_thr = scratch + (size_t)2 * nq * n_chunks * k;
+    // threshold seed: min over k row segments of the segment maximum (needs k non-empty segments), else "minus infinity"
+    const bool seed = n_rows >= 4 * k;
+    int rc = cw_check_cuda(cudaMemsetAsync(shared_thr, seed ? 0x7f : 0x80, (size_t)nq * sizeof(int), st),
+                           "cw_dense_rows_topk: memset");
+    if (rc) return rc;
+    if (seed) {
+        const int seg_len = (n_rows + k - 1) / k;
+        const int n_seg = (n_rows + seg_len - 1) / seg_len;
+        if (n_seg == k)
+            rows_segmax_kernel<<<dim3(k, (unsigned)gblocks), wpb * 32, 0, st>>>(scores, (unsigned)ldq, nq, n_rows, seg_len,
+                                                                              shared_thr);
+        else if ((rc = cw_check_cuda(cudaMemsetAsync(shared_thr, 0x80, (size_t)nq * sizeof(int), st), "cw_dense_rows_topk: memset")))
+            return rc;
+    }
+    if (smem > 48 * 1024) {
+        rc = cw_check_cuda(cudaFuncSetAttribute(rows_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                           "cw_dense_rows_topk: smem attribute");
+        if (rc) return rc;
+    }
+    rows_topk_kernel<<<dim3(n_chunks, (unsigned)gblocks), wpb * 32, smem, st>>>(scores, (unsigned)ldq, nq, n_rows, sent_off,
+                                                                             sent_ids, k, cand_s, cand_i, n_chunks, chunk_len,
+                                                                             shared_thr);
+    merge_topk_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, st>>>(cand_s, cand_i, nq, n_chunks, k, out_sid, out_score);
+    return cw_check_cuda(cudaGetLastError(), "cw_dense_rows_topk");
 }

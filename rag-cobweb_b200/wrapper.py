@@ -231,8 +231,13 @@ class DenseIndex:
                                            S.data_ptr(), fx["leaf_rec"].data_ptr(), fx["n_leaf"], None, 0, None, None, None, st),
                        "cw_tc_score_tiles (sample)")
             samp_sid, samp_val = ws["f_samp_sid"], ws["f_samp_val"]
-            _lib.check(L.cw_dense_paths_topk(C.byref(fx["flat"]), LS.data_ptr(), ldq, nq, kc, None, samp_sid.data_ptr(),
-                                             samp_val.data_ptr(), ws["scratch"].data_ptr(), st), "cw_dense_paths_topk (sample)")
+            if kc <= 32:
+                _lib.check(L.cw_dense_rows_topk(LS.data_ptr(), ldq, nq, n_s_rows, fx["sent_off"].data_ptr(),
+                                                fx["sent_ids"].data_ptr(), kc, samp_sid.data_ptr(), samp_val.data_ptr(),
+                                                ws["scratch"].data_ptr(), st), "cw_dense_rows_topk (sample)")
+            else:
+                _lib.check(L.cw_dense_paths_topk(C.byref(fx["flat"]), LS.data_ptr(), ldq, nq, kc, None, samp_sid.data_ptr(),
+                                                 samp_val.data_ptr(), ws["scratch"].data_ptr(), st), "cw_dense_paths_topk (sample)")
             sv = samp_val.view(-1)[: nq * kc].view(nq, kc)
             ss = samp_sid.view(-1)[: nq * kc].view(nq, kc)
             tau = torch.where(ss[:, kc - 1] >= 0, sv[:, kc - 1], tau)
