@@ -222,9 +222,9 @@ def _run_engine(args, wl):
     # FP32 mode = query tiles, FFMA scores, paths/top-k, merge
     launches_per_step = (5 if tensor else 4) * chunks
     if tensor and args.mode == "tf32x3f" and getattr(ix, "fx", None):
-        # query operands, internal scores, one cumulative-sum launch per level, sample scores, sample paths + merge,
-        # filter scores, select, re-score
-        launches_per_step = (8 + len(ix.fx["F"]["level_off"]) - 1) * chunks
+        # query operands, internal scores, one cumulative-sum launch per level, sample scores, sample segment-max +
+        # top-k + merge, filter scores, select, re-score
+        launches_per_step = (9 + len(ix.fx["F"]["level_off"]) - 1) * chunks
 
     store_mode = args.shard == "store" and world > 1
     if store_mode:
