@@ -359,6 +359,8 @@ class DenseIndex:
         # small batches: the fused pipeline's extra launches (one per tree level) cost more than the path kernel saves
         fused = (mode == "tf32x3f" and kc > 0 and _level == 0 and getattr(self, "fx", None) is not None and
                  Q.shape[0] >= self.FUSED_MIN_QUERIES)
+        if fused and self.fx["n_s"] == 0 and self.fx["n_leaf"] > self.FUSED_CAP:
+            fused = False  # too few leaf tiles to sample a threshold from, too many leaves for the candidate buffer
         nq_total = Q.shape[0]
         step = self.chunk_queries()
         sids = torch.empty((nq_total, max(k, 1)), dtype=torch.int32, device=Q.device)
