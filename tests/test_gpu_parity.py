@@ -617,9 +617,10 @@ def test_fused_tensor_predict_matches_fp32_path(n, d, kind, k, weights):
     assert torch.equal(a, ids32[:3]) and torch.equal(b, v32[:3])
     # candidate-buffer overflow: with 8 slots per query nearly every query overflows, is flagged by cw_tc_select and
     # answered by the unfused path -- same result
+    # (a tree without a sampled tile and with more leaves than slots skips the fused pipeline altogether)
     ix.FUSED_CAP, ix._ws, e0 = 8, None, ix.n_escalated
     a, b, _ = ix.predict(qd, k)
-    assert torch.equal(a, ids32) and torch.equal(b, v32) and ix.n_escalated - e0 > 100
+    assert torch.equal(a, ids32) and torch.equal(b, v32) and (ix.n_escalated - e0 > 100 or ix.fx["n_s"] == 0)
 
 
 def test_tensor_modes_small_and_odd_shapes():
