@@ -209,7 +209,9 @@ def _run_engine(args, wl):
     torch.cuda.synchronize()
     index_build_s = time.time() - t0
     ix = w._index
-    tensor = args.mode in ("tf32x3", "tf32x3f") and ix.candidates(k) > 0
+    tensor = args.mode in ("tf32x3", "tf32x3f") and ix.candidates(k) > 0 and ix.nn >= ix.TENSOR_MIN_NODES
+    if not tensor:
+        ix.set_mode("fp32")  # small index or k beyond the re-score kernel: the engine answers on the FP32 pipe anyway
     # this rank's batch: global batch = world * qn, contiguous shards
     q_all, targets_all = synth.queries(x, qn * world, kind, seed=1, targets=np.arange(qn * world) % docs)
     lo, hi = parallel.shard_bounds(qn * world, world, rank)

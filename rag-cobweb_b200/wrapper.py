@@ -38,6 +38,7 @@ class DenseIndex:
     MODES = ("fp32", "tf32x3", "tf32x3f")
     FUSED_CAP = 1024  # candidate slots per query of the filtering epilogue
     FUSED_MIN_QUERIES = 256
+    TENSOR_MIN_NODES = 16384  # smaller indexes are answered on the FP32 pipe (fewer launches, no read-back; same result)
     EPS_SCALE = 2.0 ** -18  # bound of |tf32x3 - fp32| leaf score relative to the operand magnitudes (cw_dense_rescore)
 
     def __init__(self, tree, leaf_of_sentence, level_weights=None, sentence_ids=None):
@@ -353,6 +354,8 @@ class DenseIndex:
             finally:
                 self.mode = prev
         tensor = mode in ("tf32x3", "tf32x3f")
+        if tensor and k > 0 and not want_leaf_scores and self.nn < self.TENSOR_MIN_NODES:
+            return self.predict(Q, k, mode="fp32")  # launch-bound at this size: the FP32 path is the shorter one
         kc = self.candidates(k, _level) if (tensor and not want_leaf_scores) else 0
         if tensor and kc == 0 and k > 0 and not want_leaf_scores:
             return self.predict(Q, k, mode="fp32")  # this k / depth is not served by the re-score kernel
@@ -429,7 +432,7 @@ class DenseIndex:
         if out_sid is None:
             out_sid = torch.empty((nq_total, k), dtype=torch.int32)
             out_val = torch.empty((nq_total, k), dtype=torch.float32)
-        if self.mode == "tf32x3f" and self.candidates(k) > 0:
+        if self.mode == "tf32x3f" and self.candidates(k) > 0 and self.nn >= self.TENSOR_MIN_NODES:
             # fused mode: pinned host batch -> device, the device pipeline, ids/scores back (no single C call yet)
             for lo in range(0, nq_total, step):
                 nq = min(step, nq_total - lo)
@@ -441,7 +444,7 @@ class DenseIndex:
                 out_val[lo:lo + nq].copy_(vd, non_blocking=True)
             torch.cuda.current_stream().synchronize()
             return out_sid, out_val
-        tensor = self.mode == "tf32x3" and self.candidates(k) > 0
+        tensor = self.mode in ("tf32x3", "tf32x3f") and self.candidates(k) > 0 and self.nn >= self.TENSOR_MIN_NODES
         nfb = (C.c_int32 * 2)(0, 0)
         for lo in range(0, nq_total, step):
             nq = min(step, nq_total - lo)

@@ -18,7 +18,9 @@ pytestmark = pytest.mark.gpu
 EPS32 = float(np.finfo(np.float32).eps)
 
 from oracle.cobweb_oracle import OracleTree, leaf_scores as oracle_leaf_scores  # noqa: E402
-from rag_cobweb_b200 import CobwebTorchTree, CobwebWrapper, synth  # noqa: E402
+from rag_cobweb_b200 import CobwebTorchTree, CobwebWrapper, DenseIndex, synth  # noqa: E402
+
+DenseIndex.TENSOR_MIN_NODES = 0  # the tests' trees are small: keep the tensor-core modes on the tensor cores
 
 
 def pos_of(b):
