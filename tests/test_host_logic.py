@@ -303,3 +303,29 @@ def test_fused_layout_reproduces_the_path_sums():
     ns = F["n_sample_tiles"]
     assert ns == len(range(0, len(F["leaf_rows"]) // 64, 4)) and len(F["flat_pos_rec"]) == F["sent_off"][ns * 64]
     assert (F["flat_pos_rec"][:, 2] < ns * 64).all() and (np.diff(F["flat_pos_rec"][:, 2]) >= 0).all()
+
+
+def test_candidate_levels_and_adaptation():
+    """Host-side policy of the tensor-core modes (no GPU needed): candidates per query at the two levels, the k range
+    served by the re-score kernel, growth of the first level when a batch escalates too often."""
+    from rag_cobweb_b200.wrapper import DenseIndex
+    ix = DenseIndex.__new__(DenseIndex)
+
+    class _Tree:
+        d = 768
+    ix.tree, ix.n_pos, ix.max_len = _Tree(), 1000, 14
+    assert ix.candidates(10) == 24 and ix.candidates(10, 1) == 64 and ix.candidates(10, 2) == 0
+    assert ix.candidates(1) == 24 and ix.candidates(16) == 24 and ix.candidates(20) == 40 and ix.candidates(32) == 64
+    assert ix.candidates(32, 1) == 0          # already at the kernel's maximum: flagged queries go to the FP32 path
+    assert ix.candidates(33) == 0 and ix.candidates(0) == 0
+    ix.max_len = 2000                          # kc * max_len beyond the re-score kernel's 16-bit slots
+    assert ix.candidates(10) == 0
+    ix.max_len = 14
+    ix._adapt(10000, 10)                       # 0.1 % escalated: keep
+    assert ix.candidates(10) == 24
+    ix._adapt(10000, 80)                       # 0.8 %: more first-level candidates
+    assert ix.candidates(10) == 32
+    ix._adapt(10000, 5000)
+    assert ix.candidates(10) == 32             # capped at the fast insertion path's 32
+    ix.n_pos = 0
+    assert ix.candidates(10) == 0
