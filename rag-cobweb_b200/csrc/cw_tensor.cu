@@ -31,6 +31,7 @@
 // outer, query tile inner) so that the panel's query operands stay in L2 while the node operands stream.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/cobweb_b200.h"
 
@@ -408,6 +409,198 @@ tc_score_kernel(const unsigned char *__restrict__ A, const unsigned char *__rest
     }
 }
 
+// ------------------------------------------------------------------ CTA-pair variant (experimental, COBWEB_B200_TC2=1)
+// The same 256 x 256 tile computed by a cluster of two CTAs with tcgen05.mma.cta_group::2: each CTA holds its own 128
+// query rows and HALF of the node rows, the accumulator of a CTA is 128 x 256 = 256 TMEM columns, so two tiles fit and
+// the epilogue of tile t overlaps the MMAs of tile t+1 (the single-CTA kernel above cannot: its tile fills TMEM).
+// Operand traffic per SM is unchanged (32 KB per 6 MMAs).  Node-score epilogue only.
+constexpr int P_PART = TM * ROWB;         // 8 KB: 128 rows of one image
+constexpr int P_STAGE = 4 * P_PART;       // A_hi, A_lo (own query rows), B_hi, B_lo (own half of the node rows)
+constexpr int P_NSTAGE = 6;
+constexpr int P_SMEM = P_NSTAGE * P_STAGE + 1024 + 512;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {  // arrives on the barrier at this offset in both CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((unsigned short)3)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+tc_score_pair_kernel(const unsigned char *__restrict__ A, const unsigned char *__restrict__ B, const TcEpi epi, int n_qtiles,
+                     int nt_begin, int n_ntiles, int n_slabs, int pq) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bars = base + P_NSTAGE * P_STAGE;
+    // full[P_NSTAGE], empty[P_NSTAGE], peer_full[P_NSTAGE] (leader), acc_full[2], acc_empty[2] (leader), TMEM base
+    const uint32_t full0 = bars, empty0 = full0 + 8 * P_NSTAGE, peer0 = empty0 + 8 * P_NSTAGE, accf0 = peer0 + 8 * P_NSTAGE;
+    const uint32_t acce0 = accf0 + 16, tmem_slot = acce0 + 16;
+    uint32_t *tmem_slot_ptr = reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < P_NSTAGE; s++) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, 1);
+            mbar_init(peer0 + 8 * s, 1);
+        }
+        for (int a = 0; a < 2; a++) {
+            mbar_init(accf0 + 8 * a, 1);
+            mbar_init(acce0 + 8 * a, 2 * (EPI_THREADS / 32));  // every epilogue warp of both CTAs
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // barriers of both CTAs are initialised before anyone signals across
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    const long long n_tiles = (long long)n_qtiles * n_ntiles;
+    const long long cid = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+    if (warp == 0) {
+        // ===== producer: own query rows + own half of the node rows
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (long long t = cid; t < n_tiles; t += n_clusters) {
+                int nt, qt;
+                tile_coords(t, n_qtiles, n_ntiles, pq, nt, qt);
+                const unsigned char *asrc = A + (size_t)qt * n_slabs * A_BYTES + rank * P_PART;
+                const unsigned char *bsrc = B + (size_t)(nt_begin + nt) * n_slabs * B_BYTES + rank * P_PART;
+                for (int s = 0; s < n_slabs; s++) {
+                    mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                    const uint32_t sb = base + stage * P_STAGE;
+                    mbar_arrive_expect_tx(full0 + 8 * stage, P_STAGE);
+                    bulk_g2s(sb, asrc + (size_t)s * A_BYTES, P_PART, full0 + 8 * stage);
+                    bulk_g2s(sb + P_PART, asrc + (size_t)s * A_BYTES + A_IMG, P_PART, full0 + 8 * stage);
+                    bulk_g2s(sb + 2 * P_PART, bsrc + (size_t)s * B_BYTES, P_PART, full0 + 8 * stage);
+                    bulk_g2s(sb + 3 * P_PART, bsrc + (size_t)s * B_BYTES + B_IMG, P_PART, full0 + 8 * stage);
+                    if (++stage == P_NSTAGE) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, aphase = 0;
+            if (leader) {
+                // ===== MMA issuer for the pair
+                constexpr uint32_t idesc = make_idesc(2 * TM, TN);
+                for (long long t = cid; t < n_tiles; t += n_clusters) {
+                    mbar_wait(acce0 + 8 * acc, aphase ^ 1);  // both CTAs have drained this accumulator
+                    tc_fence_after();
+                    const uint32_t d = tmem_base + (uint32_t)(acc * TN);
+                    for (int s = 0; s < n_slabs; s++) {
+                        mbar_wait(full0 + 8 * stage, phase);
+                        mbar_wait(peer0 + 8 * stage, phase);
+                        tc_fence_after();
+                        const uint32_t sb = base + stage * P_STAGE;
+                        const uint64_t a_hi = make_smem_desc(sb), a_lo = make_smem_desc(sb + P_PART);
+                        const uint64_t b_hi = make_smem_desc(sb + 2 * P_PART), b_lo = make_smem_desc(sb + 3 * P_PART);
+#pragma unroll
+                        for (int k = 0; k < ROWB / 32; k++) {
+                            const uint64_t ko = (uint64_t)(2 * k);
+                            tc_mma_tf32_pair(d, a_hi + ko, b_hi + ko, idesc, (s | k) != 0);
+                            tc_mma_tf32_pair(d, a_hi + ko, b_lo + ko, idesc, 1);
+                            tc_mma_tf32_pair(d, a_lo + ko, b_hi + ko, idesc, 1);
+                        }
+                        tc_commit_pair(empty0 + 8 * stage);
+                        if (s == n_slabs - 1) tc_commit_pair(accf0 + 8 * acc);
+                        if (++stage == P_NSTAGE) { stage = 0; phase ^= 1; }
+                    }
+                    if (++acc == 2) { acc = 0; aphase ^= 1; }
+                }
+            } else {
+                // ===== relay: tell the leader when this CTA's operands of a stage have landed
+                const uint32_t peer_remote = mapa_u32(peer0, 0);
+                for (long long t = cid; t < n_tiles; t += n_clusters) {
+                    for (int s = 0; s < n_slabs; s++) {
+                        mbar_wait(full0 + 8 * stage, phase);
+                        mbar_arrive_cluster(peer_remote + 8 * stage);
+                        if (++stage == P_NSTAGE) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===== epilogue (both CTAs): this CTA's 128 queries x 256 nodes of the tile
+        const int quarter = warp & 3, sub = (warp - 2) >> 2;
+        const uint32_t acce_leader = mapa_u32(acce0, 0);
+        int acc = 0;
+        uint32_t aphase = 0;
+        const long long ldq = epi.ldq;
+        for (long long t = cid; t < n_tiles; t += n_clusters) {
+            int nt, qt;
+            tile_coords(t, n_qtiles, n_ntiles, pq, nt, qt);
+            const long long n0 = (long long)(nt_begin + nt) * TN;
+            mbar_wait(accf0 + 8 * acc, aphase);
+            tc_fence_after();
+            const long long q0 = (long long)qt * TQ + rank * TM;
+            if (q0 < ldq) {
+                const long long q = q0 + quarter * 32 + lane;
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * TN);
+#pragma unroll 1
+                for (int c = sub; c < TN / 32; c += 2) {
+                    uint32_t v[32];
+                    CW_TMEM_LD32(taddr + (uint32_t)(c * 32), v);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        const long long n = n0 + c * 32 + j;
+                        epi.out[n * ldq + q] = fmaf(-0.5f, __uint_as_float(v[j]), __ldg(epi.hconst + n));
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(acce_leader + 8 * acc);
+            if (++acc == 2) { acc = 0; aphase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // the peer may still be reading this CTA's operands / signalling its barriers
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+    }
+}
+
 // ------------------------------------------------------------------ operand builders
 // Queries: Q [nq, D] -> A [q tile][slab][hi, lo][256 rows x 64 B swizzled]; row = (x^2 x8 | x x8)
 __global__ void __launch_bounds__(256)
@@ -603,7 +796,8 @@ static int tc_launch(int mode, const cw_tc_index *tx, const void *a_scratch, int
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long n_tiles = (long long)n_qtiles * nt_count;
     if (n_tiles == 0) return 0;
-    const int grid = (int)(n_tiles < sms ? n_tiles : sms);
+    int grid = (int)(n_tiles < sms ? n_tiles : sms);
+    static const bool use_pair = getenv("COBWEB_B200_TC2") && atoi(getenv("COBWEB_B200_TC2")) != 0;
     // query-tile panels: the panel's query operands (A_BYTES per tile and slab) should sit in L2 (~40 MB of it)
     // while the node operands stream through; equal-width panels
     const long long a_tile = (long long)tx->n_slabs * A_BYTES;
@@ -611,6 +805,16 @@ static int tc_launch(int mode, const cw_tc_index *tx, const void *a_scratch, int
     if (pq_max < 1) pq_max = 1;
     const int n_panels = (n_qtiles + pq_max - 1) / pq_max;
     const int pq = (n_qtiles + n_panels - 1) / n_panels;
+    if (use_pair && mode == EPI_NODE) {
+        rc = cw_check_cuda(cudaFuncSetAttribute(tc_score_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM),
+                           "cw_tc: smem attribute (pair)");
+        if (rc) return rc;
+        grid = (int)(2 * n_tiles < sms ? 2 * n_tiles : (sms & ~1));
+        tc_score_pair_kernel<<<grid, THREADS, P_SMEM, st>>>(reinterpret_cast<const unsigned char *>(a_scratch),
+                                                           reinterpret_cast<const unsigned char *>(tx->B), epi, n_qtiles,
+                                                           nt_begin, nt_count, tx->n_slabs, pq);
+        return cw_check_cuda(cudaGetLastError(), "cw_tc: pair score kernel");
+    }
     kern<<<grid, THREADS, SMEM_BYTES, st>>>(reinterpret_cast<const unsigned char *>(a_scratch),
                                             reinterpret_cast<const unsigned char *>(tx->B), epi, n_qtiles, nt_begin, nt_count,
                                             tx->n_slabs, pq);
