@@ -564,23 +564,32 @@ class CobwebWrapper:
         """CobwebWrapper.build_prediction_index (CobwebWrapper.py:91-208)."""
         if self._index is not None:
             return
-        self._index = DenseIndex(self.tree, self._leaf_of_sentence, self._level_weights).set_mode(self.dense_mode)
+        ix = DenseIndex(self.tree, self._leaf_of_sentence, self._level_weights)
+        self._index = ix.set_mode(self._resolve_mode(ix))
         self.max_depth = max(self.max_depth, self._index.max_depth)
 
-    # default scoring mode of new wrappers; "tf32x3" returns the same ids and scores faster but builds two more
-    # operand copies per index (DenseIndex.MODES)
-    dense_mode = os.environ.get("COBWEB_B200_DENSE_MODE", "fp32")
+    # Scoring mode of the dense index (DenseIndex.MODES; every mode returns the same ids and scores).  "auto": the
+    # fused tensor-core mode for indexes of AUTO_TENSOR_NODES nodes and more -- it builds two more operand copies, which
+    # 180 GB of HBM is there for -- and the FP32 pipe below (launch-bound at that size).
+    dense_mode = os.environ.get("COBWEB_B200_DENSE_MODE", "auto")
+    AUTO_TENSOR_NODES = 16384
+
+    def _resolve_mode(self, index):
+        if self.dense_mode != "auto":
+            return self.dense_mode
+        return "tf32x3f" if index.nn >= self.AUTO_TENSOR_NODES else "fp32"
 
     def set_dense_mode(self, mode):
-        """Additive: where cobweb_predict_fast / predict_fast_batch compute node scores -- "fp32" (FP32 pipe,
-        default) or "tf32x3" (tcgen05 tensor cores, split-TF32 operands).  See DenseIndex.MODES."""
-        if mode not in DenseIndex.MODES:
-            raise ValueError(f"mode must be one of {DenseIndex.MODES}")
+        """Additive: where cobweb_predict_fast / predict_fast_batch compute node scores -- "auto" (default), "fp32"
+        (FP32 pipe), "tf32x3" (tcgen05 tensor cores, split-TF32 operands), "tf32x3f" (the same, fused).  See
+        DenseIndex.MODES."""
+        if mode != "auto" and mode not in DenseIndex.MODES:
+            raise ValueError(f"mode must be 'auto' or one of {DenseIndex.MODES}")
         self.dense_mode = mode
         if self._index is not None:
-            self._index.set_mode(mode)
+            self._index.set_mode(self._resolve_mode(self._index))
         if getattr(self, "_shard_index", None) is not None:
-            self._shard_index.set_mode(mode)
+            self._shard_index.set_mode(self._resolve_mode(self._shard_index))
 
     def force_rebuild_index(self):
         self._invalidate_prediction_index()
@@ -649,7 +658,8 @@ class CobwebWrapper:
             tree_order = np.lexsort((np.arange(len(self._leaf_of_sentence)), row_of[self._leaf_of_sentence]))
             lo, hi = parallel.shard_bounds(len(tree_order), world, rank)
             self._shard_index = DenseIndex(self.tree, self._leaf_of_sentence, self._level_weights,
-                                           sentence_ids=np.sort(tree_order[lo:hi])).set_mode(self.dense_mode)
+                                           sentence_ids=np.sort(tree_order[lo:hi]))
+            self._shard_index.set_mode(self._resolve_mode(self._shard_index))
             self._shard_key = key
         Q = self.tree._as_device_mat(Q)
         kk = min(int(k), self._shard_index.n_pos, _lib.MAX_K)
