@@ -467,8 +467,7 @@ def _run_engine(args, wl):
     line = {
         "metric": "cobweb_predict_fast queries/sec", "value": total_q * args.steps / (ms_dev * 1e-3), "unit": "queries/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps,
-        "higher_is_better": True, "scaling": "strong" if store_mode else "weak", "vs_baseline": None,
-        "dtype": "f32 (results); pre-filter in split TF32 (3 x tf32 products, f32 accumulate)" if tensor else "f32",
+        "higher_is_better": True, "scaling": "strong" if store_mode else "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": cfg, "docs": docs, "dim": dim, "nodes": nn, "queries_per_gpu": qn, "k": k,
                    "parallelism": (f"store sharded x{world} (sentences + ancestor nodes), NCCL all-gather + top-k merge"
