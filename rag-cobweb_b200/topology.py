@@ -136,10 +136,9 @@ def fused_layout(order, parent_b, depth, leaf_of_sentence, level_weights=None, n
 
     The leaf score sum_j (w_j/len) s_j is rewritten as (C[parent] + w_leaf * s_leaf) / len with the cumulative
     ancestor sums C[n] = C[parent(n)] + w_depth(n) * s_n, which do not depend on the leaf.  Index rows are split
-    into internal rows (BFS order, levels contiguous) and sentence-leaf rows; the leaf rows are cut into tiles of
-    `tile` rows and every `sample_every`-th full tile is moved to the front: those tiles are scored first and give
-    every query a lower bound of its k-th best score, against which the remaining tiles are filtered in the scoring
-    kernel's epilogue.  Returns a dict of numpy arrays (rows are BFS index rows of `order`):
+    into internal rows (BFS order, levels contiguous) and sentence-leaf rows; every `sample_every`-th leaf is moved to
+    the front (whole tiles of `tile` rows): those rows are scored first and give every query a lower bound of its
+    k-th best score, against which the remaining tiles are filtered in the scoring kernel's epilogue.  Returns a dict of numpy arrays (rows are BFS index rows of `order`):
       int_rows, int_parent (internal index or -1), int_w (float32), level_off (internal rows per depth, prefix sums),
       leaf_rows (new leaf order), leaf_parent (internal index or -1), leaf_w, leaf_inv_len (float32), n_sample_tiles,
       sent_off [n_leaf + 1], sent_ids (sentence ids, ascending per leaf),
@@ -171,16 +170,19 @@ def fused_layout(order, parent_b, depth, leaf_of_sentence, level_weights=None, n
     int_w = wrow[np.minimum(int_depth, max_len - 1)].astype(np.float32)
     n_levels = int(int_depth.max()) + 1 if len(int_rows) else 0
     level_off = np.concatenate([[0], np.cumsum(np.bincount(int_depth, minlength=n_levels))]).astype(np.int64)
-    # leaf rows: BFS order, tiles, sampled full tiles first, the partial last tile last
+    # leaf rows: every `sample_every`-th leaf (in BFS order) forms the sample -- a strided sample, because BFS order
+    # keeps the leaves of a cluster together and whole tiles of neighbours would miss most clusters -- cut to whole
+    # tiles and moved to the front; the other leaves keep their BFS order (siblings adjacent: their parents' sums are
+    # read together), the partial last tile is theirs
     leaves = np.nonzero(is_leaf)[0]
     n_leaf = len(leaves)
-    n_full = n_leaf // tile
-    tiles = np.arange(n_full)
-    sampled = tiles[tiles % sample_every == 0] if n_full >= sample_every else tiles[:0]
-    rest = np.setdiff1d(tiles, sampled)
-    perm_tiles = np.concatenate([sampled, rest])
-    idx = (perm_tiles[:, None] * tile + np.arange(tile)[None, :]).reshape(-1)
-    idx = np.concatenate([idx, np.arange(n_full * tile, n_leaf)]).astype(np.int64)
+    samp = np.arange(0, n_leaf, sample_every, dtype=np.int64)
+    n_s_tiles = len(samp) // tile if n_leaf >= sample_every * tile else 0
+    samp = samp[: n_s_tiles * tile]
+    rest_mask = np.ones(n_leaf, bool)
+    rest_mask[samp] = False
+    idx = np.concatenate([samp, np.nonzero(rest_mask)[0]]).astype(np.int64)
+    sampled = np.arange(n_s_tiles)
     leaf_rows = leaves[idx]
     leaf_len = depth[leaf_rows] + 1
     leaf_parent = np.where(parent_b[leaf_rows] >= 0, int_of_row[np.maximum(parent_b[leaf_rows], 0)], -1)

@@ -301,7 +301,9 @@ def test_fused_layout_reproduces_the_path_sums():
     np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-9)
     assert sorted(F["sent_ids"].tolist()) == list(range(len(leaf_of_sentence)))
     ns = F["n_sample_tiles"]
-    assert ns == len(range(0, len(F["leaf_rows"]) // 64, 4)) and len(F["flat_pos_rec"]) == F["sent_off"][ns * 64]
+    n_leaf = len(F["leaf_rows"])
+    assert ns == ((n_leaf + 3) // 4) // 64 and ns > 0 and len(F["flat_pos_rec"]) == F["sent_off"][ns * 64]
+    assert sorted(F["leaf_rows"].tolist()) == sorted(np.unique(topology.sentence_paths(order, parent_b, depth, leaf_of_sentence, lw, n_slots=n_nodes)["pos_rec"][:, 2]).tolist())
     assert (F["flat_pos_rec"][:, 2] < ns * 64).all() and (np.diff(F["flat_pos_rec"][:, 2]) >= 0).all()
 
 
