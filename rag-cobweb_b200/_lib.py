@@ -16,14 +16,16 @@ CW_USE_INFO, CW_USE_KL, CW_ACUITY_CUTOFF = 1, 2, 4
 HDR_WORDS = 16
 SCRATCH_WORDS = 16384
 TILE_N, TILE_K, MAX_K, MAX_D, MAX_CHILDREN = 128, 16, 128, 4096, 2048
-TC_TILE_Q, TC_TILE_N, TC_SLAB_D, RESCORE_MAX_KC = 256, 256, 8, 64
 IFIT_NODE_SLACK, IFIT_POOL_SLACK = 160, 16384
+H_TILE, H_F1, H_F2 = 256, 1, 2
+FUSED_MAX_K, FUSED_FB_ROUNDS, SMALL_Q, SID_UNRESOLVED, FUSED_STATS = 30, 2, 32, -2, 12
 
 EXPORTS = ["cw_version", "cw_last_error", "cw_store_init", "cw_ifit", "cw_set_ifit_cluster", "cw_categorize_ctas", "cw_categorize",
            "cw_index_build", "cw_xt_floats", "cw_score_ldq", "cw_dense_node_scores", "cw_topk_chunks", "cw_dense_paths_topk",
-           "cw_predict_dense_host", "cw_tc_b_bytes", "cw_tc_a_bytes", "cw_tc_index_build",
-           "cw_dense_node_scores_tc", "cw_tc_build_queries", "cw_tc_score_tiles", "cw_tc_cumsum_level", "cw_tc_select", "cw_dense_rows_topk",
-           "cw_rescore_smem_bytes", "cw_rescore_rows_build", "cw_dense_rescore", "cw_rank_scores_bwd", "cw_whiten", "cw_ffma_peak", "cw_ffma2_peak"]
+           "cw_predict_dense_host", "cw_index_rows_build",
+           "cw_h_b_bytes", "cw_h_a_bytes", "cw_h_stages", "cw_h_set_build", "cw_h_rows_isotropic", "cw_fused_predict",
+           "cw_fused_predict_host", "cw_small_scratch_words", "cw_small_predict", "cw_small_predict_host",
+           "cw_rank_scores_bwd", "cw_whiten", "cw_ffma_peak", "cw_ffma2_peak"]
 
 
 class CwStore(C.Structure):
@@ -41,17 +43,32 @@ class CwIndex(C.Structure):
                 ("path_idx", C.c_void_p), ("level_w", C.c_void_p), ("pos_rec", C.c_void_p)]
 
 
-class CwTcIndex(C.Structure):
-    _fields_ = [("D", C.c_int32), ("nn", C.c_int32), ("n_ntiles", C.c_int32), ("n_slabs", C.c_int32),
-                ("B", C.c_void_p), ("hconst", C.c_void_p), ("rows", C.c_void_p), ("pos_of_sid", C.c_void_p),
-                ("hmax", C.c_float), ("lmax", C.c_float), ("wfac", C.c_float), ("eps_scale", C.c_float)]
-
-
 class CwDenseWork(C.Structure):
     _fields_ = [("Q_dev", C.c_void_p), ("xt_scratch", C.c_void_p), ("node_scores", C.c_void_p), ("ldq", C.c_int64),
-                ("out_sid_dev", C.c_void_p), ("out_score_dev", C.c_void_p), ("scratch", C.c_void_p),
-                ("cand_sid", C.c_void_p), ("cand_score", C.c_void_p), ("fail", C.c_void_p), ("kc", C.c_int32),
-                ("kc2", C.c_int32)]
+                ("out_sid_dev", C.c_void_p), ("out_score_dev", C.c_void_p), ("scratch", C.c_void_p)]
+
+
+class CwHSet(C.Structure):
+    _fields_ = [("n_rows", C.c_int32), ("n_ntiles", C.c_int32), ("n_stages", C.c_int32), ("nprod", C.c_int32),
+                ("layout", C.c_int32), ("reserved", C.c_int32), ("B", C.c_void_p), ("rc", C.c_void_p)]
+
+
+class CwFusedIndex(C.Structure):
+    _fields_ = [("ix", CwIndex), ("n_int", C.c_int32), ("n_leaf", C.c_int32), ("n_sample_tiles", C.c_int32),
+                ("n_levels", C.c_int32), ("internal", CwHSet), ("leaves", CwHSet),
+                ("int_parent", C.c_void_p), ("int_w", C.c_void_p), ("level_off", C.c_void_p), ("leaf_row_b", C.c_void_p),
+                ("leaf_pos", C.c_void_p), ("sent_off", C.c_void_p), ("sent_ids", C.c_void_p), ("rows", C.c_void_p),
+                ("e1max", C.c_float), ("hmax", C.c_float), ("lmax", C.c_float), ("wfac", C.c_float), ("eps_scale", C.c_float),
+                ("prior_var", C.c_float)]
+
+
+class CwFusedWork(C.Structure):
+    _fields_ = [("cap_q", C.c_int64), ("ldq", C.c_int64), ("Q_dev", C.c_void_p), ("A_int", C.c_void_p), ("A_leaf", C.c_void_p),
+                ("qv", C.c_void_p), ("S", C.c_void_p), ("slots", C.c_void_p), ("tau", C.c_void_p), ("cap", C.c_int32),
+                ("reserved", C.c_int32), ("cnt", C.c_void_p), ("cand_val", C.c_void_p), ("cand_row", C.c_void_p),
+                ("flag", C.c_void_p), ("out_sid_dev", C.c_void_p), ("out_val_dev", C.c_void_p), ("sm_Q", C.c_void_p),
+                ("sm_scores", C.c_void_p), ("sm_scratch", C.c_void_p), ("sm_sid", C.c_void_p), ("sm_val", C.c_void_p),
+                ("sm_n", C.c_void_p), ("stats", C.c_void_p), ("audit_every", C.c_int32), ("audit_phase", C.c_int32)]
 
 
 class CobwebB200Error(RuntimeError):
@@ -88,25 +105,23 @@ def load():
     L.cw_topk_chunks.restype = i64
     L.cw_topk_chunks.argtypes = [i64]
     L.cw_dense_paths_topk.argtypes = [C.POINTER(CwIndex), vp, i64, i64, i32, vp, vp, vp, vp, vp]
-    L.cw_predict_dense_host.argtypes = [C.POINTER(CwIndex), C.POINTER(CwTcIndex), C.POINTER(CwStore), vp, i64, i32,
-                                        C.POINTER(CwDenseWork), vp, vp, C.POINTER(C.c_int32), vp]
-    L.cw_tc_build_queries.argtypes = [C.POINTER(CwTcIndex), vp, i64, vp, vp]
-    L.cw_tc_score_tiles.argtypes = [C.POINTER(CwTcIndex), vp, i64, i32, C.c_int32, C.c_int32, vp, i64, vp, vp, C.c_int32, vp,
-                                    C.c_int32, vp, vp, vp, vp]
-    L.cw_tc_cumsum_level.argtypes = [vp, i64, C.c_int32, C.c_int32, vp, vp, vp]
-    L.cw_tc_select.argtypes = [i64, i32, vp, vp, C.c_int32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
-    L.cw_dense_rows_topk.argtypes = [vp, i64, i64, C.c_int32, vp, vp, i32, vp, vp, vp, vp]
-    L.cw_rescore_smem_bytes.restype = i64
-    L.cw_rescore_smem_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32]
-    L.cw_rescore_rows_build.argtypes = [C.POINTER(CwStore), vp, C.c_int32, vp, vp]
-    L.cw_dense_rescore.argtypes = [C.POINTER(CwStore), C.POINTER(CwIndex), vp, vp, vp, i64, i32, vp, vp, i32, C.c_float,
-                                   C.c_float, C.c_float, C.c_float, vp, vp, vp, vp]
-    L.cw_tc_b_bytes.restype = i64
-    L.cw_tc_b_bytes.argtypes = [C.c_int32, C.c_int32]
-    L.cw_tc_a_bytes.restype = i64
-    L.cw_tc_a_bytes.argtypes = [i64, C.c_int32]
-    L.cw_tc_index_build.argtypes = [C.POINTER(CwStore), vp, C.c_int32, vp, C.POINTER(CwTcIndex), vp]
-    L.cw_dense_node_scores_tc.argtypes = [C.POINTER(CwTcIndex), vp, i64, vp, vp, i64, vp]
+    L.cw_predict_dense_host.argtypes = [C.POINTER(CwIndex), C.POINTER(CwDenseWork), vp, i64, i32, vp, vp, vp]
+    L.cw_index_rows_build.argtypes = [C.POINTER(CwStore), vp, C.c_int32, vp, vp]
+    i32c = C.c_int32
+    L.cw_h_b_bytes.restype = i64
+    L.cw_h_b_bytes.argtypes = [i32c, i32c, i32c, i32c]
+    L.cw_h_a_bytes.restype = i64
+    L.cw_h_a_bytes.argtypes = [i64, i32c, i32c, i32c]
+    L.cw_h_stages.restype = i32c
+    L.cw_h_stages.argtypes = [i32c, i32c, i32c]
+    L.cw_h_set_build.argtypes = [C.POINTER(CwStore), vp, vp, vp, C.POINTER(CwHSet), vp, vp, vp, vp, vp]
+    L.cw_h_rows_isotropic.argtypes = [C.POINTER(CwStore), vp, vp, i32c, vp, vp]
+    L.cw_fused_predict.argtypes = [C.POINTER(CwFusedIndex), C.POINTER(CwFusedWork), vp, i64, i32, vp, vp, vp]
+    L.cw_fused_predict_host.argtypes = [C.POINTER(CwFusedIndex), C.POINTER(CwFusedWork), vp, i64, i32, vp, vp, vp, vp]
+    L.cw_small_scratch_words.restype = i64
+    L.cw_small_scratch_words.argtypes = [i64, i32]
+    L.cw_small_predict.argtypes = [C.POINTER(CwIndex), vp, i64, vp, vp, i32c, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.cw_small_predict_host.argtypes = [C.POINTER(CwIndex), vp, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.cw_rank_scores_bwd.argtypes = [C.POINTER(CwIndex), vp, i64, vp, vp, i64, vp, vp]
     L.cw_whiten.argtypes = [vp, i64, C.c_int32, vp, vp, C.c_int32, vp, vp, vp, vp, vp]
     L.cw_ffma_peak.argtypes = [i32, i32, i32, vp, vp]

@@ -19,8 +19,7 @@ UNITS = [
     ("cw_categorize.cu", ["-fmad=false"]),
     ("cw_index.cu", ["-fmad=false"]),
     ("cw_dense.cu", []),
-    ("cw_tensor.cu", []),
-    ("cw_rescore.cu", ["-fmad=false"]),
+    ("cw_half.cu", []),
     ("cw_whiten.cu", []),
     ("cw_grad.cu", []),
 ]

@@ -287,8 +287,9 @@ __global__ void __launch_bounds__(256, 3)
 paths_topk_kernel(const float *__restrict__ ST, unsigned ldq, long long nq, int n_pos, int max_len,
                   const int *__restrict__ path_pm, const int4 *__restrict__ pos_rec,
                   const double *__restrict__ level_w, int k, float *leaf_scores, float *cand_s, int *cand_i,
-                  int n_chunks, int chunk_len, int *shared_thr) {
+                  int n_chunks, int chunk_len, int *shared_thr, const int *__restrict__ nq_dev) {
     extern __shared__ __align__(16) unsigned char pt_smem[];
+    if (nq_dev) nq = min(nq, (long long)*nq_dev);  // count decided on the device (flagged queries of the fused mode)
     // level weights in binary64; the path weight of level j on a path of length len is
     // (float)(level_w[j] / len), the fp32 value the reference stores in its sparse path matrix
     double *lw = reinterpret_cast<double *>(pt_smem);  // [max_len]
@@ -495,108 +496,6 @@ paths_topk_kernel(const float *__restrict__ ST, unsigned ldq, long long nq, int 
     }
 }
 
-// ------------------------------------------------------------------ top-k over the rows of a leaf-score matrix
-// Used by the fused tensor mode for its sample of the leaves: S[row * ldq + q] already is the leaf score, a row's
-// sentences are sent_ids[sent_off[row] .. sent_off[row + 1]).  Same list handling as the path kernel (per-lane
-// sorted k-lists in shared memory behind a register threshold, k <= 32, per-chunk lists merged afterwards, k-th-best
-// bound shared between the chunks) without any path bookkeeping: eight independent row loads in flight per warp.
-// Pre-pass of rows_topk_kernel: the rows are cut into k contiguous segments; the smallest of the k segment maxima
-// is a lower bound of the k-th best score (k different rows reach it), so it can seed the threshold the chunks
-// share and spare every chunk the k ln(n/k) insertions of a cold list.  grid (k segments, query-group blocks).
-__global__ void __launch_bounds__(256)
-rows_segmax_kernel(const float *__restrict__ S, unsigned ldq, long long nq, int n_rows, int seg_len, int *shared_thr) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    const long long g = (long long)blockIdx.y * wpb + warp;
-    if (g * 32 >= nq) return;
-    const long long q = g * 32 + lane;
-    const bool qvalid = q < nq;
-    const float *col = S + (qvalid ? q : g * 32);
-    const int r0 = blockIdx.x * seg_len, r1 = min(n_rows, r0 + seg_len);
-    float m[8];
-#pragma unroll
-    for (int i = 0; i < 8; i++) m[i] = -__int_as_float(0x7f800000);
-    for (int rb = r0; rb < r1; rb += 8) {
-#pragma unroll
-        for (int i = 0; i < 8; i++)
-            if (rb + i < r1) m[i] = fmaxf(m[i], col[(size_t)(unsigned)(rb + i) * ldq]);
-    }
-    float mx = fmaxf(fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])), fmaxf(fmaxf(m[4], m[5]), fmaxf(m[6], m[7])));
-    if (qvalid && r1 > r0) atomicMin(shared_thr + q, float_key(mx));
-}
-
-__global__ void __launch_bounds__(256)
-rows_topk_kernel(const float *__restrict__ S, unsigned ldq, long long nq, int n_rows, const int *__restrict__ sent_off,
-                 const int *__restrict__ sent_ids, int k, float *cand_s, int *cand_i, int n_chunks, int chunk_len,
-                 int *shared_thr) {
-    extern __shared__ __align__(16) unsigned char rt_smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    float *Ls = reinterpret_cast<float *>(rt_smem) + (size_t)warp * k * 32;
-    int *Li = reinterpret_cast<int *>(reinterpret_cast<float *>(rt_smem) + (size_t)wpb * k * 32) + (size_t)warp * k * 32;
-    const float NEG_INF = -__int_as_float(0x7f800000);
-    for (int i = lane; i < 32 * k; i += 32) { Ls[i] = NEG_INF; Li[i] = -1; }
-    __syncwarp();
-    const long long g = (long long)blockIdx.y * wpb + warp;
-    if (g * 32 >= nq) return;
-    const long long q = g * 32 + lane;
-    const bool qvalid = q < nq;
-    const float *col = S + (qvalid ? q : g * 32);
-    const int chunk = blockIdx.x;
-    const int r0 = chunk * chunk_len, r1 = min(n_rows, r0 + chunk_len);
-    float thr_s = NEG_INF, gthr = NEG_INF, published = NEG_INF;
-    int thr_i = 0x7fffffff;
-    int *gslot = shared_thr + (qvalid ? q : 0);
-    for (int rb = r0; rb < r1; rb += 8) {
-        float v[8];
-#pragma unroll
-        for (int i = 0; i < 8; i++) v[i] = rb + i < r1 ? col[(size_t)(unsigned)(rb + i) * ldq] : NEG_INF;
-        if (qvalid) {
-            if (thr_i != 0x7fffffff && thr_s > published) {
-                published = thr_s;
-                atomicMax(gslot, float_key(thr_s));
-            }
-            gthr = fmaxf(gthr, key_float(__ldcg(gslot)));
-        }
-#pragma unroll 1
-        for (int i = 0; i < 8; i++) {
-            const int row = rb + i;
-            if (row >= r1) break;
-            const float acc = v[i];
-            const int s0 = sent_off[row], s1 = sent_off[row + 1];
-            for (int s = s0; s < s1; s++) {
-                const int sid = sent_ids[s];
-                unsigned need = __ballot_sync(0xffffffffu, qvalid && acc >= gthr &&
-                                                               (acc > thr_s || (acc == thr_s && (unsigned)sid < (unsigned)thr_i)));
-                while (need) {  // one rank per lane: read, ballot the insertion point, shift by one, done
-                    const int L = __ffs(need) - 1;
-                    need &= need - 1;
-                    const float cv = __shfl_sync(0xffffffffu, acc, L);
-                    const int base = L * k;
-                    float es = NEG_INF;
-                    int ei = -1;
-                    if (lane < k) { es = Ls[base + lane]; ei = Li[base + lane]; }
-                    const int pos = __popc(__ballot_sync(0xffffffffu, es > cv || (es == cv && ei < sid)));
-                    const float ps = __shfl_sync(0xffffffffu, es, (k - 2) & 31);
-                    const int pi = __shfl_sync(0xffffffffu, ei, (k - 2) & 31);
-                    if (lane >= pos && lane + 1 < k) { Ls[base + lane + 1] = es; Li[base + lane + 1] = ei; }
-                    if (lane == pos) { Ls[base + lane] = cv; Li[base + lane] = sid; }
-                    if (lane == L) {
-                        const bool cand_last = (k < 2) || (pos == k - 1);
-                        thr_s = cand_last ? cv : ps;
-                        thr_i = cand_last ? sid : pi;
-                        if (thr_i < 0) thr_i = 0x7fffffff;
-                    }
-                    __syncwarp();
-                }
-            }
-        }
-    }
-    if (qvalid) {
-        float *os = cand_s + (q * n_chunks + chunk) * k;
-        int *oi = cand_i + (q * n_chunks + chunk) * k;
-        for (int r = 0; r < k; r++) { os[r] = Ls[lane * k + r]; oi[r] = Li[lane * k + r]; }
-    }
-}
-
 // Running top-k of one warp, kept sorted across the lanes: rank r lives in lane r%32, slot r/32
 // (register arrays ls/li, fully unrolled).  Used to merge the per-chunk candidate lists.
 __device__ __forceinline__ void topk_init(float (&ls)[PT_SLOTS], int (&li)[PT_SLOTS]) {
@@ -658,8 +557,9 @@ __device__ __forceinline__ void topk_store(const float (&ls)[PT_SLOTS], const in
 // grid (ceil(nq/8)): warp w merges the n_chunks*k candidates of one query into the final k
 __global__ void __launch_bounds__(256)
 merge_topk_kernel(const float *__restrict__ cand_s, const int *__restrict__ cand_i, long long nq, int n_chunks, int k,
-                  int *out_sid, float *out_score) {
+                  int *out_sid, float *out_score, const int *__restrict__ nq_dev = nullptr) {
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (nq_dev) nq = min(nq, (long long)*nq_dev);
     const long long q = (long long)blockIdx.x * 8 + w;
     if (q >= nq) return;
     const int n = n_chunks * k;
@@ -718,18 +618,17 @@ extern "C" int cw_dense_node_scores(const cw_index *ix, const float *Q, int64_t 
 // one extra chunk worth of scratch holds the per-query thresholds shared between the chunks
 extern "C" int64_t cw_topk_chunks(int64_t n_pos) { return (n_pos + 1023) / 1024 + 1; }
 
-extern "C" int cw_dense_paths_topk(const cw_index *ix, const float *node_scores, int64_t ldq, int64_t nq, int k,
-                                   float *leaf_scores, int32_t *out_sid, float *out_score, int32_t *scratch,
-                                   void *stream) {
+// nq_dev (optional): the number of live queries is read on the device (<= nq, which sizes the launch)
+static int paths_topk_launch(const cw_index *ix, const float *node_scores, int64_t ldq, int64_t nq, int k, float *leaf_scores,
+                             int32_t *out_sid, float *out_score, int32_t *scratch, const int *nq_dev, cudaStream_t st) {
     if (!ix || !node_scores || nq < 0 || k < 0 || k > CW_MAX_K || ix->n_pos < 1 || !ix->path_idx || !ix->pos_rec ||
-        !ix->level_w || ix->max_len < 1 || ix->max_len > PT_MAXLEN || ldq < cw_score_ldq(nq) || ldq > 0x7fffffffLL ||
+        !ix->level_w || ix->max_len < 1 || ix->max_len > PT_MAXLEN || ldq < nq || ldq > 0x7fffffffLL ||
         (k > 0 && (!out_sid || !out_score || !scratch))) {
         cw_set_error("cw_dense_paths_topk: bad argument (k=%d max %d, max_len=%d max %d)", k, CW_MAX_K,
                      ix ? ix->max_len : -1, PT_MAXLEN);
         return CW_E_ARG;
     }
     if (nq == 0) return 0;
-    cudaStream_t st = (cudaStream_t)stream;
     // warps per CTA: per warp the per-lane top-k lists take k*256 bytes of shared memory, the partial-sum
     // stack max_len*128 bytes, the record and prefetch rings 5 KB; pick the CTA size that keeps most warps per SM
     const size_t per_warp = (size_t)k * 256 + (size_t)ix->max_len * 132 + PF_RECS * sizeof(PathRec) +
@@ -780,171 +679,193 @@ extern "C" int cw_dense_paths_topk(const cw_index *ix, const float *node_scores,
     }
     kern<<<dim3(n_chunks, (unsigned)gblocks), wpb * 32, smem, st>>>(
         node_scores, (unsigned)ldq, nq, ix->n_pos, ix->max_len, ix->path_idx, reinterpret_cast<const int4 *>(ix->pos_rec),
-        ix->level_w, k, leaf_scores, cand_s, cand_i, n_chunks, chunk_len, shared_thr);
+        ix->level_w, k, leaf_scores, cand_s, cand_i, n_chunks, chunk_len, shared_thr, nq_dev);
     if (k > 0)
-        merge_topk_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, st>>>(cand_s, cand_i, nq, n_chunks, k, out_sid, out_score);
+        merge_topk_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, st>>>(cand_s, cand_i, nq, n_chunks, k, out_sid, out_score, nq_dev);
     return cw_check_cuda(cudaGetLastError(), "cw_dense_paths_topk");
 }
 
-// FP32-pipe answer for nq queries already in Q_dev: scores, paths, top-k, results into the device buffers
-static int fp32_predict(const cw_index *ix, const cw_dense_work *w, int64_t nq, int k, void *stream) {
-    const int64_t ldq = cw_score_ldq(nq);
-    int rc = cw_dense_node_scores(ix, w->Q_dev, nq, reinterpret_cast<float *>(w->xt_scratch), w->node_scores, ldq, stream);
-    if (rc) return rc;
-    return cw_dense_paths_topk(ix, w->node_scores, ldq, nq, k, nullptr, w->out_sid_dev, w->out_score_dev, w->scratch, stream);
-}
-
-// Tensor-core answer for nq queries already in Q_dev: pre-filter scores, top-kc candidates, exact re-score;
-// flagged queries are listed in w->fail
-static int tensor_predict(const cw_index *ix, const cw_tc_index *tx, const cw_store *s, const cw_dense_work *w, int64_t nq,
-                          int k, int kc, void *stream) {
-    const int64_t ldq = cw_score_ldq(nq);
-    int rc = cw_dense_node_scores_tc(tx, w->Q_dev, nq, w->xt_scratch, w->node_scores, ldq, stream);
-    if (rc) return rc;
-    if ((rc = cw_dense_paths_topk(ix, w->node_scores, ldq, nq, kc, nullptr, w->cand_sid, w->cand_score, w->scratch, stream)))
-        return rc;
-    return cw_dense_rescore(s, ix, tx->rows, tx->pos_of_sid, w->Q_dev, nq, kc, w->cand_sid, w->cand_score, k, tx->hmax, tx->lmax,
-                            tx->wfac, tx->eps_scale, w->out_sid_dev, w->out_score_dev, w->fail, stream);
-}
-
-// flagged list of the last tensor_predict -> host, ascending; returns the count (or a negative error)
-static int fetch_flagged(const cw_dense_work *w, int32_t **list, cudaStream_t st) {
-    int32_t n = 0;
-    int rc = cw_check_cuda(cudaMemcpyAsync(&n, w->fail, sizeof(int32_t), cudaMemcpyDeviceToHost, st), "flagged count");
-    if (!rc) rc = cw_check_cuda(cudaStreamSynchronize(st), "flagged count sync");
-    if (rc) return rc;
-    *list = nullptr;
-    if (n <= 0) return 0;
-    int32_t *l = new int32_t[n];
-    rc = cw_check_cuda(cudaMemcpy(l, w->fail + 1, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost), "flagged list");
-    if (rc) { delete[] l; return rc; }
-    for (int i = 1; i < n; i++) {  // insertion sort: the kernel appends in nearly ascending order
-        const int32_t v = l[i];
-        int j = i - 1;
-        for (; j >= 0 && l[j] > v; j--) l[j + 1] = l[j];
-        l[j + 1] = v;
-    }
-    *list = l;
-    return n;
-}
-
-extern "C" int cw_predict_dense_host(const cw_index *ix, const cw_tc_index *tx, const cw_store *s, const float *Q_host,
-                                     int64_t nq, int k, const cw_dense_work *w, int32_t *out_sid_host,
-                                     float *out_score_host, int32_t *stats, void *stream) {
-    if (!ix || !Q_host || !w || !w->Q_dev || !out_sid_host || !out_score_host || k < 1 ||
-        (tx && (!s || !w->cand_sid || !w->cand_score || !w->fail || w->kc <= k))) {
-        cw_set_error("cw_predict_dense_host: bad argument");
+extern "C" int cw_dense_paths_topk(const cw_index *ix, const float *node_scores, int64_t ldq, int64_t nq, int k,
+                                   float *leaf_scores, int32_t *out_sid, float *out_score, int32_t *scratch,
+                                   void *stream) {
+    if (ldq < cw_score_ldq(nq)) {
+        cw_set_error("cw_dense_paths_topk: ldq must be >= cw_score_ldq(nq)");
         return CW_E_ARG;
     }
-    cudaStream_t st = (cudaStream_t)stream;
-    if (stats) stats[0] = stats[1] = 0;
-    const size_t row_i = (size_t)k * sizeof(int32_t), row_f = (size_t)k * sizeof(float), qrow = (size_t)ix->D * sizeof(float);
-    int rc = cw_check_cuda(cudaMemcpyAsync(w->Q_dev, Q_host, (size_t)nq * qrow, cudaMemcpyHostToDevice, st),
-                           "cw_predict_dense_host: H2D");
-    if (rc) return rc;
-    rc = tx ? tensor_predict(ix, tx, s, w, nq, k, w->kc, stream) : fp32_predict(ix, w, nq, k, stream);
-    if (rc) return rc;
-    rc = cw_check_cuda(cudaMemcpyAsync(out_sid_host, w->out_sid_dev, (size_t)nq * row_i, cudaMemcpyDeviceToHost, st),
-                       "cw_predict_dense_host: D2H ids");
-    if (rc) return rc;
-    rc = cw_check_cuda(cudaMemcpyAsync(out_score_host, w->out_score_dev, (size_t)nq * row_f, cudaMemcpyDeviceToHost, st),
-                       "cw_predict_dense_host: D2H scores");
-    if (rc) return rc;
-    if (!tx) return cw_check_cuda(cudaStreamSynchronize(st), "cw_predict_dense_host: sync");
-
-    // Flagged queries (rare): their rows are compacted to the front of Q_dev (ascending, so no row is overwritten
-    // before it is moved), answered again -- first with kc2 candidates, what is still flagged on the FP32 pipe --
-    // and the rows scattered back to their places in the host result.
-    int32_t *list = nullptr;
-    int n_fail = fetch_flagged(w, &list, st);  // synchronises: the first-pass results are on the host
-    if (n_fail <= 0) return n_fail;
-    auto compact = [&](const int32_t *src_rows, int n) {
-        for (int i = 0; i < n; i++)
-            if (src_rows[i] != i)
-                cudaMemcpyAsync(w->Q_dev + (size_t)i * ix->D, w->Q_dev + (size_t)src_rows[i] * ix->D, qrow, cudaMemcpyDeviceToDevice, st);
-    };
-    auto scatter = [&](int dev_row, int host_row) {
-        cudaMemcpyAsync(out_sid_host + (size_t)host_row * k, w->out_sid_dev + (size_t)dev_row * k, row_i, cudaMemcpyDeviceToHost, st);
-        cudaMemcpyAsync(out_score_host + (size_t)host_row * k, w->out_score_dev + (size_t)dev_row * k, row_f, cudaMemcpyDeviceToHost, st);
-    };
-    compact(list, n_fail);
-    if (w->kc2 > w->kc) {
-        if (stats) stats[0] = n_fail;
-        rc = tensor_predict(ix, tx, s, w, n_fail, k, w->kc2, stream);
-        int32_t *list2 = nullptr;
-        const int n2 = rc ? rc : fetch_flagged(w, &list2, st);
-        if (n2 < 0) { delete[] list; return n2; }
-        for (int i = 0, j = 0; i < n_fail; i++) {  // rows decided at this level go home
-            if (j < n2 && list2[j] == i) { j++; continue; }
-            scatter(i, list[i]);
-        }
-        if ((rc = cw_check_cuda(cudaStreamSynchronize(st), "cw_predict_dense_host: escalation sync"))) n_fail = 0;
-        if (n2 > 0 && !rc) {
-            compact(list2, n2);
-            for (int j = 0; j < n2; j++) list[j] = list[list2[j]];
-        }
-        delete[] list2;
-        if (rc) { delete[] list; return rc; }
-        n_fail = n2;
-    }
-    if (n_fail > 0) {
-        if (stats) stats[1] = n_fail;
-        rc = fp32_predict(ix, w, n_fail, k, stream);
-        for (int i = 0; i < n_fail && !rc; i++) scatter(i, list[i]);
-        if (!rc) rc = cw_check_cuda(cudaStreamSynchronize(st), "cw_predict_dense_host: fallback sync");
-    }
-    delete[] list;
-    return rc;
+    return paths_topk_launch(ix, node_scores, ldq, nq, k, leaf_scores, out_sid, out_score, scratch, nullptr, (cudaStream_t)stream);
 }
 
-extern "C" int cw_dense_rows_topk(const float *scores, int64_t ldq, int64_t nq, int32_t n_rows, const int32_t *sent_off,
-                                  const int32_t *sent_ids, int k, int32_t *out_sid, float *out_score, int32_t *scratch,
-                                  void *stream) {
-    if (!scores || !sent_off || !sent_ids || !out_sid || !out_score || !scratch || nq < 0 || n_rows < 1 || k < 1 || k > 32 ||
-        ldq < cw_score_ldq(nq) || ldq > 0x7fffffffLL) {
-        cw_set_error("cw_dense_rows_topk: bad argument (k=%d, 1..32)", k);
+// One call = batched cobweb_predict_fast(return_ids=True) on HOST buffers with the FP32 form
+extern "C" int cw_predict_dense_host(const cw_index *ix, const cw_dense_work *w, const float *Q_host, int64_t nq, int k,
+                                     int32_t *out_sid_host, float *out_score_host, void *stream) {
+    if (!ix || !Q_host || !w || !w->Q_dev || !w->xt_scratch || !w->node_scores || !w->out_sid_dev || !w->out_score_dev ||
+        !w->scratch || !out_sid_host || !out_score_host || k < 1 || nq < 0) {
+        cw_set_error("cw_predict_dense_host: bad argument");
         return CW_E_ARG;
     }
     if (nq == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    int dev = 0, sms = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int wpb = 8;
-    const size_t smem = (size_t)wpb * k * 256;
-    int ctas = (int)((227 * 1024) / (smem + 1024));
-    if (ctas > 8) ctas = 8;
-    const long long groups = (nq + 31) / 32, gblocks = (groups + wpb - 1) / wpb;
-    long long want = (long long)sms * ctas / gblocks;
-    const long long max_chunks = cw_topk_chunks(n_rows) - 1;
-    if (want > max_chunks) want = max_chunks;
-    if (want < 1) want = 1;
-    const int chunk_len = (int)((n_rows + want - 1) / want);
-    const int n_chunks = (n_rows + chunk_len - 1) / chunk_len;
-    float *cand_s = reinterpret_cast<float *>(scratch);
-    int *cand_i = scratch + (size_t)nq * n_chunks * k;
-    int *shared_thr = scratch + (size_t)2 * nq * n_chunks * k;
-    // threshold seed: min over k row segments of the segment maximum (needs k non-empty segments), else "minus infinity"
-    const bool seed = n_rows >= 4 * k;
-    int rc = cw_check_cuda(cudaMemsetAsync(shared_thr, seed ? 0x7f : 0x80, (size_t)nq * sizeof(int), st),
-                           "cw_dense_rows_topk: memset");
+    int rc = cw_check_cuda(cudaMemcpyAsync(w->Q_dev, Q_host, (size_t)nq * ix->D * sizeof(float), cudaMemcpyHostToDevice, st),
+                           "cw_predict_dense_host: H2D");
     if (rc) return rc;
-    if (seed) {
-        const int seg_len = (n_rows + k - 1) / k;
-        const int n_seg = (n_rows + seg_len - 1) / seg_len;
-        if (n_seg == k)
-            rows_segmax_kernel<<<dim3(k, (unsigned)gblocks), wpb * 32, 0, st>>>(scores, (unsigned)ldq, nq, n_rows, seg_len,
-                                                                              shared_thr);
-        else if ((rc = cw_check_cuda(cudaMemsetAsync(shared_thr, 0x80, (size_t)nq * sizeof(int), st), "cw_dense_rows_topk: memset")))
-            return rc;
+    const int64_t ldq = cw_score_ldq(nq);
+    if ((rc = cw_dense_node_scores(ix, w->Q_dev, nq, reinterpret_cast<float *>(w->xt_scratch), w->node_scores, ldq, stream))) return rc;
+    if ((rc = cw_dense_paths_topk(ix, w->node_scores, ldq, nq, k, nullptr, w->out_sid_dev, w->out_score_dev, w->scratch, stream)))
+        return rc;
+    if ((rc = cw_check_cuda(cudaMemcpyAsync(out_sid_host, w->out_sid_dev, (size_t)nq * k * sizeof(int32_t), cudaMemcpyDeviceToHost, st),
+                            "cw_predict_dense_host: D2H ids")))
+        return rc;
+    if ((rc = cw_check_cuda(cudaMemcpyAsync(out_score_host, w->out_score_dev, (size_t)nq * k * sizeof(float),
+                                            cudaMemcpyDeviceToHost, st), "cw_predict_dense_host: D2H scores")))
+        return rc;
+    return cw_check_cuda(cudaStreamSynchronize(st), "cw_predict_dense_host: sync");
+}
+
+// ------------------------------------------------------------------ exact small-batch path
+// nq <= CW_SMALL_Q queries against every node with the arithmetic of dense_score_kernel (per (query, node): d ascending,
+// u = fma(x, r, mb); acc = fma(u, u, acc)), but laid out for a HANDFUL of queries: thread = node, the R / MB tiles are
+// streamed once with coalesced loads (16 attributes = 32 loads in flight per thread), the queries sit in shared
+// memory.  One query is HBM-bound (8 bytes per node and attribute); 32 queries are FMA-bound.  Serves single-query
+// cobweb_predict_fast and the flagged queries of the fused mode.
+namespace cw {
+constexpr int SM_DC = 256;  // attributes of the queries staged in shared memory at a time
+
+template <int QB>
+__global__ void __launch_bounds__(CW_TILE_N)
+small_scores_kernel(const float *__restrict__ XQ, const float *__restrict__ R, const float *__restrict__ MB,
+                    const float *__restrict__ sumlog, float *__restrict__ out, int n_ktiles, int D, int nq,
+                    const int *__restrict__ nq_dev) {
+    __shared__ __align__(16) float xs[SM_DC * QB];
+    if (nq_dev) nq = min(nq, *nq_dev);
+    if (nq <= 0) return;
+    const int nt = blockIdx.x, nl = threadIdx.x;
+    float acc[QB];
+#pragma unroll
+    for (int q = 0; q < QB; q++) acc[q] = 0.0f;
+    const float *rsrc = R + (size_t)nt * n_ktiles * (TK * TN) + nl;
+    const float *msrc = MB + (size_t)nt * n_ktiles * (TK * TN) + nl;
+    for (int kt0 = 0; kt0 < n_ktiles; kt0 += SM_DC / TK) {
+        const int d0 = kt0 * TK;
+        __syncthreads();
+        for (int i = threadIdx.x; i < SM_DC * QB; i += CW_TILE_N) {
+            const int q = i / SM_DC, dd = i % SM_DC;  // consecutive threads read consecutive attributes of one query
+            xs[dd * QB + q] = (q < nq && d0 + dd < D) ? XQ[(size_t)q * D + d0 + dd] : 0.0f;
+        }
+        __syncthreads();
+        const int kt1 = min(n_ktiles, kt0 + SM_DC / TK);
+        for (int kt = kt0; kt < kt1; kt++) {
+            float r[TK], m[TK];
+#pragma unroll
+            for (int kk = 0; kk < TK; kk++) {
+                r[kk] = rsrc[((size_t)kt * TK + kk) * TN];
+                m[kk] = msrc[((size_t)kt * TK + kk) * TN];
+            }
+#pragma unroll
+            for (int kk = 0; kk < TK; kk++) {
+                const float *xr = xs + ((kt - kt0) * TK + kk) * QB;
+#pragma unroll
+                for (int q = 0; q < QB; q++) {
+                    const float u = __fmaf_rn(xr[q], r[kk], m[kk]);
+                    acc[q] = __fmaf_rn(u, u, acc[q]);
+                }
+            }
+        }
     }
-    if (smem > 48 * 1024) {
-        rc = cw_check_cuda(cudaFuncSetAttribute(rows_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                           "cw_dense_rows_topk: smem attribute");
-        if (rc) return rc;
+    const int b = nt * TN + nl;
+    const float sl = sumlog[b];
+#pragma unroll
+    for (int q = 0; q < QB; q++) out[(size_t)b * CW_SMALL_Q + q] = -0.5f * (sl + acc[q]);
+}
+
+__global__ void small_gather_kernel(const float *__restrict__ Q, int D, const int *__restrict__ which, const int *__restrict__ n_dev,
+                                    int off, int nq_max, float *sm_Q, int *sm_n) {
+    int n = nq_max;
+    if (n_dev) n = max(0, min(nq_max, *n_dev - off));
+    if (blockIdx.x == 0 && threadIdx.x == 0) *sm_n = n;
+    const long long total = (long long)n * D;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int q = (int)(i / D), d = (int)(i % D);
+        sm_Q[i] = Q[(size_t)which[off + q] * D + d];
     }
-    rows_topk_kernel<<<dim3(n_chunks, (unsigned)gblocks), wpb * 32, smem, st>>>(scores, (unsigned)ldq, nq, n_rows, sent_off,
-                                                                             sent_ids, k, cand_s, cand_i, n_chunks, chunk_len,
-                                                                             shared_thr);
-    merge_topk_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, st>>>(cand_s, cand_i, nq, n_chunks, k, out_sid, out_score);
-    return cw_check_cuda(cudaGetLastError(), "cw_dense_rows_topk");
+}
+__global__ void small_scatter_kernel(const int *__restrict__ which, int off, const int *__restrict__ sm_n, int k,
+                                     const int *__restrict__ sm_sid, const float *__restrict__ sm_val, int *out_sid, float *out_val) {
+    const int n = *sm_n;
+    for (int i = threadIdx.x; i < n * k; i += blockDim.x) {
+        const int q = i / k, j = i % k;
+        const size_t dst = (size_t)which[off + q] * k + j;
+        out_sid[dst] = sm_sid[i];
+        out_val[dst] = sm_val[i];
+    }
+}
+}  // namespace cw
+
+extern "C" int64_t cw_small_scratch_words(int64_t n_pos, int k) {
+    return (int64_t)CW_SMALL_Q * cw_topk_chunks(n_pos < 1 ? 1 : n_pos) * (k > 0 ? k : 1) * 2;
+}
+
+int cw_small_predict_impl(const cw_index *ix, const float *Q, int64_t nq, const int32_t *which, const int32_t *n_dev,
+                          int32_t which_off, int scatter, int k, float *sm_Q, float *sm_scores, int32_t *sm_scratch, int32_t *sm_sid,
+                          float *sm_val, int32_t *sm_n, int32_t *out_sid, float *out_val, cudaStream_t st) {
+    if (!ix || !Q || nq < 0 || nq > CW_SMALL_Q || k < 1 || k > CW_MAX_K || !sm_scores || !sm_scratch || !out_sid || !out_val ||
+        (which && (!sm_Q || !sm_sid || !sm_val || !sm_n)) || (n_dev && !which)) {
+        cw_set_error("cw_small_predict: bad argument (nq=%lld, at most %d; k=%d)", (long long)nq, CW_SMALL_Q, k);
+        return CW_E_ARG;
+    }
+    if (nq == 0) return 0;
+    const float *xq = Q;
+    const int *cnt = nullptr;
+    if (which) {
+        small_gather_kernel<<<32, 256, 0, st>>>(Q, ix->D, which, n_dev, which_off, (int)nq, sm_Q, sm_n);
+        xq = sm_Q;
+        cnt = sm_n;
+    }
+    const int qb = n_dev ? CW_SMALL_Q : (nq <= 1 ? 1 : nq <= 2 ? 2 : nq <= 4 ? 4 : nq <= 8 ? 8 : nq <= 16 ? 16 : 32);
+    auto launch = [&](auto kern) {
+        kern<<<ix->n_ntiles, CW_TILE_N, 0, st>>>(xq, ix->R, ix->MB, ix->sumlog, sm_scores, ix->n_ktiles, ix->D, (int)nq, cnt);
+    };
+    switch (qb) {
+        case 1: launch(small_scores_kernel<1>); break;
+        case 2: launch(small_scores_kernel<2>); break;
+        case 4: launch(small_scores_kernel<4>); break;
+        case 8: launch(small_scores_kernel<8>); break;
+        case 16: launch(small_scores_kernel<16>); break;
+        default: launch(small_scores_kernel<32>); break;
+    }
+    int rc = paths_topk_launch(ix, sm_scores, CW_SMALL_Q, nq, k, nullptr, which ? sm_sid : out_sid, which ? sm_val : out_val,
+                               sm_scratch, cnt, st);
+    if (rc) return rc;
+    if (which && scatter) small_scatter_kernel<<<1, 256, 0, st>>>(which, which_off, sm_n, k, sm_sid, sm_val, out_sid, out_val);
+    return cw_check_cuda(cudaGetLastError(), "cw_small_predict");
+}
+
+extern "C" int cw_small_predict(const cw_index *ix, const float *Q, int64_t nq, const int32_t *which, const int32_t *n_dev,
+                                int32_t which_off, int scatter, int k, float *sm_Q, float *sm_scores, int32_t *sm_scratch, int32_t *sm_sid,
+                                float *sm_val, int32_t *sm_n, int32_t *out_sid, float *out_val, void *stream) {
+    return cw_small_predict_impl(ix, Q, nq, which, n_dev, which_off, scatter, k, sm_Q, sm_scores, sm_scratch, sm_sid, sm_val, sm_n, out_sid,
+                                 out_val, (cudaStream_t)stream);
+}
+
+extern "C" int cw_small_predict_host(const cw_index *ix, const float *Q_host, int64_t nq, int k, float *sm_Q, float *sm_scores,
+                                     int32_t *sm_scratch, int32_t *sm_sid, float *sm_val, int32_t *sm_n, int32_t *out_sid_host,
+                                     float *out_val_host, void *stream) {
+    if (!ix || !Q_host || !sm_Q || !sm_sid || !sm_val || !out_sid_host || !out_val_host || nq < 0 || nq > CW_SMALL_Q) {
+        cw_set_error("cw_small_predict_host: bad argument");
+        return CW_E_ARG;
+    }
+    if (nq == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = cw_check_cuda(cudaMemcpyAsync(sm_Q, Q_host, (size_t)nq * ix->D * sizeof(float), cudaMemcpyHostToDevice, st),
+                           "cw_small_predict_host: H2D");
+    if (rc) return rc;
+    if ((rc = cw_small_predict_impl(ix, sm_Q, nq, nullptr, nullptr, 0, 0, k, sm_Q, sm_scores, sm_scratch, sm_sid, sm_val, sm_n, sm_sid,
+                                    sm_val, st)))
+        return rc;
+    if ((rc = cw_check_cuda(cudaMemcpyAsync(out_sid_host, sm_sid, (size_t)nq * k * sizeof(int32_t), cudaMemcpyDeviceToHost, st),
+                            "cw_small_predict_host: D2H ids")))
+        return rc;
+    if ((rc = cw_check_cuda(cudaMemcpyAsync(out_val_host, sm_val, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, st),
+                            "cw_small_predict_host: D2H scores")))
+        return rc;
+    return cw_check_cuda(cudaStreamSynchronize(st), "cw_small_predict_host: sync");
 }

@@ -82,6 +82,23 @@ index_tiles_kernel(cw_store s, const int *__restrict__ order, int nn, int n_ktil
     }
 }
 
+// RM[b, d] = {r, mb} of index row b (node order[b]), row-major
+__global__ void __launch_bounds__(256)
+index_rows_kernel(cw_store s, const int *__restrict__ order, int nn, float2 *RM) {
+    const int D = s.D;
+    const bool cutoff = (s.flags & CW_ACUITY_CUTOFF) != 0;
+    const float prior = s.prior_var;
+    for (int b = blockIdx.x; b < nn; b += gridDim.x) {
+        const int node = order[b];
+        const float cnt = s.count[node];
+        for (int d = threadIdx.x; d < D; d += blockDim.x) {
+            float r, mb;
+            dense_operands(s.mean[(size_t)node * D + d], s.m2[(size_t)node * D + d], cnt, prior, cutoff, r, mb);
+            RM[(size_t)b * D + d] = make_float2(r, mb);
+        }
+    }
+}
+
 }  // namespace cw
 
 void cw_set_error(const char *fmt, ...);
@@ -102,4 +119,14 @@ extern "C" int cw_index_build(const cw_store *s, const int32_t *order, int32_t n
     dim3 g2(ix->n_ntiles, ix->n_ktiles);
     cw::index_tiles_kernel<<<g2, 256, 0, (cudaStream_t)stream>>>(*s, order, nn, ix->n_ktiles, ix->R, ix->MB);
     return cw_check_cuda(cudaGetLastError(), "cw_index_build");
+}
+
+extern "C" int cw_index_rows_build(const cw_store *s, const int32_t *order, int32_t nn, float *rows, void *stream) {
+    if (!s || !order || !rows || nn < 1) {
+        cw_set_error("cw_index_rows_build: bad argument");
+        return CW_E_ARG;
+    }
+    cw::index_rows_kernel<<<nn < 148 * 16 ? nn : 148 * 16, 256, 0, (cudaStream_t)stream>>>(*s, order, nn,
+                                                                                          reinterpret_cast<float2 *>(rows));
+    return cw_check_cuda(cudaGetLastError(), "cw_index_rows_build");
 }

@@ -140,7 +140,7 @@ def fused_layout(order, parent_b, depth, leaf_of_sentence, level_weights=None, n
     the front (whole tiles of `tile` rows): those rows are scored first and give every query a lower bound of its
     k-th best score, against which the remaining tiles are filtered in the scoring kernel's epilogue.  Returns a dict of numpy arrays (rows are BFS index rows of `order`):
       int_rows, int_parent (internal index or -1), int_w (float32), level_off (internal rows per depth, prefix sums),
-      leaf_rows (new leaf order), leaf_parent (internal index or -1), leaf_w, leaf_inv_len (float32), n_sample_tiles,
+      leaf_rows (new leaf order), leaf_parent (internal index or -1), leaf_w, leaf_inv_len (float32), leaf_len, n_sample_tiles,
       sent_off [n_leaf + 1], sent_ids (sentence ids, ascending per leaf),
       flat_pos_rec [n_pos_s, 4], flat_path [n_pos_s, 1] (flat index over the sentences of the sampled leaves)."""
     order = np.asarray(order, np.int64)
@@ -205,6 +205,7 @@ def fused_layout(order, parent_b, depth, leaf_of_sentence, level_weights=None, n
     flat_pos_rec = np.stack([np.ones(n_pos_s, np.int64), same, flat_leaf, sent_ids[:n_pos_s]], axis=1).astype(np.int32)
     return dict(int_rows=int_rows, int_parent=int_parent.astype(np.int32), int_w=int_w, level_off=level_off,
                 leaf_rows=leaf_rows, leaf_parent=leaf_parent.astype(np.int32), leaf_w=leaf_w, leaf_inv_len=leaf_inv_len,
+                leaf_len=leaf_len.astype(np.int32),
                 n_sample_tiles=int(len(sampled)), sent_off=sent_off.astype(np.int32), sent_ids=sent_ids.astype(np.int32),
                 flat_pos_rec=np.ascontiguousarray(flat_pos_rec), flat_path=flat_leaf.astype(np.int32).reshape(-1, 1),
                 max_len=max_len)

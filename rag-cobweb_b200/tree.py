@@ -149,6 +149,8 @@ class CobwebTorchTree:
             _lib.CW_ACUITY_CUTOFF if self.acuity_cutoff else 0)
         self.store = NodeStore(dims[0], pv, flags, device=self.device)
         self._sent = {}     # node id -> SentenceList
+        self._sent_stale = False   # a wrapper added sentences since _sent was built (CobwebWrapper._record)
+        self._sent_loader = None
         self._frontier = None
         self.last_trace = None
 
@@ -164,6 +166,7 @@ class CobwebTorchTree:
     def clear(self):
         self.store.clear()
         self._sent = {}
+        self._sent_stale = False
 
     def __str__(self):
         return f"CobwebTorchTree(D={self.d}, nodes={self.num_nodes()})"
@@ -187,7 +190,14 @@ class CobwebTorchTree:
         return X.contiguous()
 
     # ------------------------------------------------------------------ sentence bookkeeping
+    def _sync_sentences(self):
+        """Bring node.sentence_id lists up to date with the wrapper's sentence -> leaf map."""
+        if self._sent_stale and self._sent_loader is not None:
+            self._sent = self._sent_loader()
+        self._sent_stale = False
+
     def _sentence_list(self, node_id):
+        self._sync_sentences()
         lst = self._sent.get(node_id)
         if lst is None:
             lst = self._sent[node_id] = SentenceList(self, node_id)
@@ -235,12 +245,12 @@ class CobwebTorchTree:
             if status == _lib.CW_E_CAPACITY:
                 self.store.reserve(max(chunk, 4096) * 2, h=h)
                 self.store.hdr[_lib.HDR_STATUS] = 0
-            elif status == _lib.CW_E_FANOUT:
-                raise _lib.CobwebB200Error(f"a node exceeded {_lib.MAX_CHILDREN} children (unsupported fan-out)")
-            elif status != 0:
-                raise _lib.CobwebB200Error(f"cw_ifit kernel status {status}")
-            elif done < chunk:
-                raise _lib.CobwebB200Error("cw_ifit stopped early without a status")
+            elif status != 0 or done < chunk:
+                msg = (f"a node exceeded {_lib.MAX_CHILDREN} children (unsupported fan-out)" if status == _lib.CW_E_FANOUT
+                       else f"cw_ifit kernel status {status}" if status else "cw_ifit stopped early without a status")
+                err = _lib.CobwebB200Error(msg)
+                err.completed, err.leaves = pos, leaves[:pos]   # rows [0, pos) are in the tree
+                raise err
         if trace:
             ops = np.concatenate(tr_parts) if tr_parts else np.zeros(0, np.int8)
             offs, base = [np.zeros(1, np.int64)], 0
@@ -345,6 +355,7 @@ class CobwebTorchTree:
 
     # ------------------------------------------------------------------ JSON
     def _sentence_ids_by_node(self):
+        self._sync_sentences()
         return {nid: list(lst) for nid, lst in self._sent.items() if len(lst)}
 
     def dump_json(self):

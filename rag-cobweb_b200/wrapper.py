@@ -28,18 +28,19 @@ class DenseIndex:
     """Device-resident prediction index (build_prediction_index, CobwebWrapper.py:91-208)."""
 
     SCORE_BUDGET_BYTES = 16 << 30  # node-score scratch per query chunk
-    # where the node scores are computed: "fp32" = FP32 pipe, (x*r + mb)^2 per triple (cw_dense.cu);
-    # "tf32x3" = tcgen05 contraction with hi/lo-split TF32 operands (cw_tensor.cu, ~1e-6 relative to "fp32") as a
-    # pre-filter for top-kc candidates, followed by the exact re-score (cw_rescore.cu): top-k ids and scores are
-    # bit-identical to "fp32"; raw node / leaf score matrices in this mode are the approximate ones
-    # "tf32x3f" = the same pre-filter with the path sums fused into the score kernel (cumulative ancestor sums +
-    # leaf scores in the epilogue, candidates filtered against a per-query bound from a sample of the leaves): the
-    # [nodes, queries] score matrix and the path kernel disappear for the leaves; same exact re-score, same results
-    MODES = ("fp32", "tf32x3", "tf32x3f")
-    FUSED_CAP = 1024  # candidate slots per query of the filtering epilogue
-    FUSED_MIN_QUERIES = 256
-    TENSOR_MIN_NODES = 16384  # smaller indexes are answered on the FP32 pipe (fewer launches, no read-back; same result)
-    EPS_SCALE = 2.0 ** -18  # bound of |tf32x3 - fp32| leaf score relative to the operand magnitudes (cw_dense_rescore)
+    # How the top-k of a query batch is computed (ids and scores are the same bit for bit in both modes):
+    #   "fp32"   every (query, node) score on the FP32 pipe, (x*r + mb)^2 per triple (cw_dense.cu), path product and
+    #            top-k over the [nodes, queries] score matrix: the form that DEFINES the result;
+    #   "fused"  tcgen05 fp16 pipeline (cw_half.cu): internal rows with split operands (hi + lo, three products) ->
+    #            cumulative ancestor sums; leaf rows with ONE fp16 product as a filter with a derived error bound;
+    #            the survivors are re-scored with the FP32 form's exact arithmetic; queries the device cannot decide
+    #            (and an always-on audit sample) go through the exact small-batch path.
+    # Batches of up to SMALL_Q queries take the exact small-batch path in every mode (one query: HBM-bound).
+    MODES = ("fp32", "fused")
+    FUSED_CAP = 1024              # candidate slots per query of the filtering epilogue
+    TENSOR_MIN_NODES = 16384      # smaller indexes are answered on the FP32 pipe (launch-bound there; same result)
+    EPS_SCALE = 2.0 ** -18        # |fp16x3 ancestor sums - fp32| relative to the operand magnitudes (cw_half.cu eps_of)
+    AUDIT_EVERY = 2048            # one query in AUDIT_EVERY is answered again by the exact path and compared (0 = off)
 
     def __init__(self, tree, leaf_of_sentence, level_weights=None, sentence_ids=None):
         """leaf_of_sentence[i] = leaf node id of sentence i.  sentence_ids (optional, sorted global
@@ -51,6 +52,8 @@ class DenseIndex:
         t = tree.store.topology()
         order, parent_b, depth = topology.bfs_order(t["root"], t["child_off"], t["child_cnt"], t["child_pool"])
         leaf_of_sentence = np.asarray(leaf_of_sentence)
+        if len(leaf_of_sentence) and int(leaf_of_sentence.min()) < 0:
+            raise ValueError("a sentence has no leaf (leaf_of_sentence < 0): the sentence list and the tree do not match")
         self.sentence_ids = None
         if sentence_ids is not None:
             self.sentence_ids = np.asarray(sentence_ids, np.int64)
@@ -63,9 +66,7 @@ class DenseIndex:
         d = tree.d
         self.n_ntiles = (self.nn + _lib.TILE_N - 1) // _lib.TILE_N
         self.n_ktiles = (d + _lib.TILE_K - 1) // _lib.TILE_K
-        # rows of the node-major score matrix (covers the 128-row tiles of the FP32 kernel and the 256-row
-        # tiles of the tensor-core kernel)
-        self.ld = (self.nn + _lib.TC_TILE_N - 1) // _lib.TC_TILE_N * _lib.TC_TILE_N
+        self.ld = self.n_ntiles * _lib.TILE_N  # rows of the node-major score matrix
         tile_elems = self.n_ntiles * self.n_ktiles * _lib.TILE_K * _lib.TILE_N
         self.R = torch.empty(tile_elems, dtype=torch.float32, device=dev)
         self.MB = torch.empty(tile_elems, dtype=torch.float32, device=dev)
@@ -80,6 +81,9 @@ class DenseIndex:
             self.max_len = p["max_len"]
             self.path_idx = torch.as_tensor(np.ascontiguousarray(p["path_idx"].T), device=dev)  # [n_pos, max_len]
             self.level_w = torch.as_tensor(p["level_w"], dtype=torch.float64, device=dev)
+            self._level_w_host = np.asarray(p["level_w"], np.float64)
+            self._pos_leaf_row = p["pos_rec"][:, 2].copy()   # ascending: positions are sorted by leaf row
+            self._path_lens = np.unique(p["pos_rec"][:, 0])
             if self.sentence_ids is not None:
                 p["pos_rec"][:, 3] = self.sentence_ids[p["pos_rec"][:, 3]]  # local position ids -> global ids
             self.pos_rec = torch.as_tensor(p["pos_rec"], device=dev)  # [n_pos, 4]
@@ -89,191 +93,115 @@ class DenseIndex:
         _lib.check(L.cw_index_build(tree.store.struct(), self.order.data_ptr(), self.nn, C.byref(ix), _lib.stream_ptr()),
                    "cw_index_build")
         self._ws = None
-        self.tx = None
+        self._sm = None
+        self._hws = None
+        self.hx = None
         self.mode = "fp32"
+        self.eps_scale = self.EPS_SCALE
+        self.audit_every = self.AUDIT_EVERY
+        self._audit_phase = 0
+        self.stats = {"queries": 0, "flagged": 0, "unresolved": 0, "cand_overflow": 0, "line_fail": 0, "list_overflow": 0,
+                      "candidates": 0, "audited": 0, "audit_mismatch": 0}
 
+    # ------------------------------------------------------------------ modes
     def set_mode(self, mode):
-        """Select the scoring kernel for predict / predict_host / node_scores; builds the tensor-core
-        operands (cw_tc_index_build) on first use."""
+        """Select how predict / predict_host compute the top-k; "fused" builds its operand sets on first use."""
         if mode not in self.MODES:
             raise ValueError(f"mode must be one of {self.MODES}")
-        if mode == "tf32x3f":
-            self.set_mode("tf32x3")
+        if mode == "fused":
             if not self.n_pos:
                 return self
-            if getattr(self, "fx", None) is None:
+            if self.hx is None:
                 self._build_fused()
-            self.mode = mode
-            return self
-        if mode == "tf32x3" and self.tx is None:
-            L, dev, d = _lib.load(), self.tree.device, self.tree.d
-            tx = _lib.CwTcIndex()
-            tx.D, tx.nn = d, self.nn
-            tx.n_ntiles = (self.nn + _lib.TC_TILE_N - 1) // _lib.TC_TILE_N
-            tx.n_slabs = (d + _lib.TC_SLAB_D - 1) // _lib.TC_SLAB_D
-            self.tcB = torch.empty(L.cw_tc_b_bytes(self.nn, d), dtype=torch.uint8, device=dev)
-            self.hconst = torch.empty(tx.n_ntiles * _lib.TC_TILE_N, dtype=torch.float32, device=dev)
-            tx.B, tx.hconst = self.tcB.data_ptr(), self.hconst.data_ptr()
-            _lib.check(L.cw_tc_index_build(self.tree.store.struct(), self.order.data_ptr(), self.nn, self.sumlog.data_ptr(),
-                                           C.byref(tx), _lib.stream_ptr()), "cw_tc_index_build")
-            # constants of the re-score margin: hmax = max_b sum_d mean^2/var (= -2 h - sumlog), lmax = max_b |sumlog|,
-            # wfac = max over path lengths of sum_j |level_w[j]| / len
-            sl = self.sumlog[: self.nn].double()
-            tx.hmax = float((-2.0 * self.hconst[: self.nn].double() - sl).max().clamp_min(0.0)) * (1.0 + 1e-6) + 1e-6
-            tx.lmax = float(sl.abs().max())
-            tx.wfac, tx.eps_scale = 1.0, self.EPS_SCALE
-            if self.n_pos:
-                rec = self.pos_rec.cpu().numpy()
-                cw = np.cumsum(np.abs(self.level_w.cpu().numpy()))
-                lens = np.unique(rec[:, 0])
-                tx.wfac = float(max(1.0, (cw[lens - 1] / lens).max()))
-                pos_of_sid = np.full(int(rec[:, 3].max()) + 1, -1, np.int32)
-                pos_of_sid[rec[:, 3]] = np.arange(len(rec), dtype=np.int32)
-                self.pos_of_sid = torch.as_tensor(pos_of_sid, device=dev)
-                tx.pos_of_sid = self.pos_of_sid.data_ptr()
-            self.rows = torch.empty((self.nn, d, 2), dtype=torch.float32, device=dev)
-            _lib.check(L.cw_rescore_rows_build(self.tree.store.struct(), self.order.data_ptr(), self.nn, self.rows.data_ptr(),
-                                               _lib.stream_ptr()), "cw_rescore_rows_build")
-            tx.rows = self.rows.data_ptr()
-            self.tx = tx
         self.mode = mode
         return self
 
+    def fused_ready(self, k):
+        """True if a top-k request is served by the fused pipeline (else: the FP32 form)."""
+        return (self.mode == "fused" and self.hx is not None and 1 <= k <= _lib.FUSED_MAX_K and
+                self.nn >= self.TENSOR_MIN_NODES and self.hx["smem_ok"])
+
     def _build_fused(self):
-        """Operands of the fused mode: separate score-kernel operand sets for the internal and the leaf rows
-        (topology.fused_layout), per-leaf records, the flat index over the sampled leaves."""
+        """Operands of the fused mode: fp16 operand sets for the internal rows (hi + lo) and the leaf rows (hi), per-leaf
+        records, row-major {r, mb} rows for the exact arithmetic, the constants of eps (topology.fused_layout)."""
         L, dev, d = _lib.load(), self.tree.device, self.tree.d
         parent_b, depth, leaf_of_sentence, level_weights, n_used = self._topo
         F = topology.fused_layout(self.order_host, parent_b, depth, leaf_of_sentence, level_weights, n_slots=n_used,
-                                  sentence_ids=self.sentence_ids, tile=_lib.TC_TILE_N)
-        order_np = np.asarray(self.order_host, np.int64)
-        fx = {"F": F, "n_int": len(F["int_rows"]), "n_leaf": len(F["leaf_rows"]), "n_s": F["n_sample_tiles"]}
+                                  sentence_ids=self.sentence_ids, tile=_lib.H_TILE)
+        st, store = _lib.stream_ptr(), self.tree.store.struct()
+        n_int, n_leaf = len(F["int_rows"]), len(F["leaf_rows"])
+        hx = {"F": F, "n_int": n_int, "n_leaf": n_leaf, "n_s": int(F["n_sample_tiles"])}
+        i32 = lambda a: torch.as_tensor(np.ascontiguousarray(a, np.int32), device=dev)
+        f32 = lambda a: torch.as_tensor(np.ascontiguousarray(a, np.float32), device=dev)
+        hx["leaf_rows"] = i32(F["leaf_rows"])
+        flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        iso = L.cw_h_rows_isotropic(store, self.order.data_ptr(), hx["leaf_rows"].data_ptr(), n_leaf, flag.data_ptr(), st)
+        if iso < 0:
+            _lib.check(iso, "cw_h_rows_isotropic")
+        hx["leaf_layout"] = _lib.H_F1 if iso == 1 else _lib.H_F2
 
-        def tc_index(rows):
-            tx = _lib.CwTcIndex()
-            tx.D, tx.nn = d, len(rows)
-            tx.n_ntiles = (len(rows) + _lib.TC_TILE_N - 1) // _lib.TC_TILE_N
-            tx.n_slabs = (d + _lib.TC_SLAB_D - 1) // _lib.TC_SLAB_D
-            B = torch.empty(L.cw_tc_b_bytes(len(rows), d), dtype=torch.uint8, device=dev)
-            h = torch.empty(tx.n_ntiles * _lib.TC_TILE_N, dtype=torch.float32, device=dev)
-            od = torch.as_tensor(order_np[rows].astype(np.int32), device=dev)
-            sl = self.sumlog[torch.as_tensor(rows, device=dev)].contiguous()
-            tx.B, tx.hconst = B.data_ptr(), h.data_ptr()
-            _lib.check(L.cw_tc_index_build(self.tree.store.struct(), od.data_ptr(), len(rows), sl.data_ptr(), C.byref(tx),
-                                           _lib.stream_ptr()), "cw_tc_index_build")
-            torch.cuda.current_stream().synchronize()  # od / sl may be freed after this
-            return tx, B, h
+        def hset(rows_t, n_rows, layout, nprod, leaf):
+            hs = _lib.CwHSet()
+            hs.n_rows, hs.n_ntiles = n_rows, (n_rows + _lib.H_TILE - 1) // _lib.H_TILE
+            hs.n_stages, hs.nprod, hs.layout = L.cw_h_stages(d, layout, nprod), nprod, layout
+            B = torch.empty(L.cw_h_b_bytes(n_rows, d, layout, nprod), dtype=torch.uint8, device=dev)
+            rc = torch.empty(hs.n_ntiles * _lib.H_TILE * (2 if nprod == 3 else 8), dtype=torch.float32, device=dev)
+            hs.B, hs.rc = B.data_ptr(), rc.data_ptr()
+            ptrs = [t.data_ptr() for t in leaf] if leaf else [None] * 4
+            _lib.check(L.cw_h_set_build(store, self.order.data_ptr(), rows_t.data_ptr(), self.sumlog.data_ptr(), C.byref(hs),
+                                        *ptrs, st), "cw_h_set_build")
+            return hs, B, rc
 
-        if fx["n_int"]:
-            fx["tx_int"], fx["B_int"], fx["h_int"] = tc_index(F["int_rows"])
-            fx["int_parent"] = torch.as_tensor(F["int_parent"], device=dev)
-            fx["int_w"] = torch.as_tensor(F["int_w"], device=dev)
-        fx["tx_leaf"], fx["B_leaf"], fx["h_leaf"] = tc_index(F["leaf_rows"])
-        n_pad = fx["tx_leaf"].n_ntiles * _lib.TC_TILE_N
-        rec = torch.zeros((n_pad, 4), dtype=torch.float32, device=dev)
-        nl = fx["n_leaf"]
-        rec[:nl, 0] = fx["h_leaf"][:nl]
-        rec[:nl, 1] = torch.as_tensor(F["leaf_w"], device=dev)
-        rec[:nl, 2] = torch.as_tensor(F["leaf_inv_len"], device=dev)
-        par = torch.full((n_pad,), -1, dtype=torch.int32, device=dev)
-        par[:nl] = torch.as_tensor(F["leaf_parent"], device=dev)
-        rec[:, 3] = par.view(torch.float32)
-        fx["leaf_rec"] = rec
-        fx["sent_off"] = torch.as_tensor(F["sent_off"], device=dev)
-        fx["sent_ids"] = torch.as_tensor(F["sent_ids"], device=dev)
-        if fx["n_s"]:
-            flat = _lib.CwIndex()
-            flat.D, flat.nn, flat.n_pos, flat.max_len = d, fx["n_s"] * _lib.TC_TILE_N, len(F["flat_pos_rec"]), 1
-            fx["flat_path"] = torch.as_tensor(F["flat_path"], device=dev)
-            fx["flat_rec"] = torch.as_tensor(F["flat_pos_rec"], device=dev)
-            fx["flat_w"] = torch.ones(1, dtype=torch.float64, device=dev)
-            flat.path_idx, flat.pos_rec, flat.level_w = fx["flat_path"].data_ptr(), fx["flat_rec"].data_ptr(), fx["flat_w"].data_ptr()
-            fx["flat"] = flat
-        self.fx = fx
-
-    def _fused_candidates(self, q, nq, kc, ws):
-        """Top-kc candidates (sentence ids + approximate leaf scores, best first) of the fused mode into
-        ws["cand_sid"] / ws["cand_val"]; returns the overflow flags [nq]."""
-        L, fx, dev = _lib.load(), self.fx, self.tree.device
-        T, ldq, st = _lib.TC_TILE_N, ws["ldq"], _lib.stream_ptr()
-        n_int_pad = (fx["n_int"] + T - 1) // T * T
-        n_s_rows = fx["n_s"] * T
-        scores = ws["scores"]
-        if scores.shape[0] < n_int_pad + n_s_rows:
-            ws["fused_extra"] = ws.get("fused_extra") if ws.get("fused_extra") is not None and ws["fused_extra"].shape[0] >= n_s_rows \
-                else torch.empty((max(n_s_rows, 1), ldq), dtype=torch.float32, device=dev)
-            LS = ws["fused_extra"]
-        else:
-            LS = scores[n_int_pad:n_int_pad + max(n_s_rows, 1)]
-        S = scores[:max(n_int_pad, 1)]
-        cap = self.FUSED_CAP
-        if ws.get("f_cap_q", 0) < nq:
-            ws["f_val"] = torch.empty((ws["cap_q"], cap), dtype=torch.float32, device=dev)
-            ws["f_row"] = torch.empty((ws["cap_q"], cap), dtype=torch.int32, device=dev)
-            ws["f_cnt"] = torch.zeros(ws["cap_q"], dtype=torch.int32, device=dev)
-            ws["f_ovf"] = torch.zeros(ws["cap_q"], dtype=torch.int32, device=dev)
-            ws["f_samp_sid"] = torch.empty((ws["cap_q"], ws["cand_sid"].shape[1]), dtype=torch.int32, device=dev)
-            ws["f_samp_val"] = torch.empty((ws["cap_q"], ws["cand_sid"].shape[1]), dtype=torch.float32, device=dev)
-            ws["f_cap_q"] = ws["cap_q"]
-        tx_leaf = fx["tx_leaf"]
-        _lib.check(L.cw_tc_build_queries(C.byref(tx_leaf), q.data_ptr(), nq, ws["xt"].data_ptr(), st), "cw_tc_build_queries")
-        if fx["n_int"]:
-            tx_int = fx["tx_int"]
-            _lib.check(L.cw_tc_score_tiles(C.byref(tx_int), ws["xt"].data_ptr(), nq, 0, 0, tx_int.n_ntiles, S.data_ptr(), ldq,
-                                           None, None, 0, None, 0, None, None, None, st), "cw_tc_score_tiles (internal)")
-            off = fx["F"]["level_off"]
-            for lvl in range(len(off) - 1):
-                _lib.check(L.cw_tc_cumsum_level(S.data_ptr(), ldq, int(off[lvl]), int(off[lvl + 1]), fx["int_parent"].data_ptr(),
-                                                fx["int_w"].data_ptr(), st), "cw_tc_cumsum_level")
-        tau = torch.full((nq,), float("-inf"), dtype=torch.float32, device=dev)
-        samp_sid = samp_val = None
-        if fx["n_s"]:
-            _lib.check(L.cw_tc_score_tiles(C.byref(tx_leaf), ws["xt"].data_ptr(), nq, 1, 0, fx["n_s"], LS.data_ptr(), ldq,
-                                           S.data_ptr(), fx["leaf_rec"].data_ptr(), fx["n_leaf"], None, 0, None, None, None, st),
-                       "cw_tc_score_tiles (sample)")
-            samp_sid, samp_val = ws["f_samp_sid"], ws["f_samp_val"]
-            if kc <= 32:
-                _lib.check(L.cw_dense_rows_topk(LS.data_ptr(), ldq, nq, n_s_rows, fx["sent_off"].data_ptr(),
-                                                fx["sent_ids"].data_ptr(), kc, samp_sid.data_ptr(), samp_val.data_ptr(),
-                                                ws["scratch"].data_ptr(), st), "cw_dense_rows_topk (sample)")
-            else:
-                _lib.check(L.cw_dense_paths_topk(C.byref(fx["flat"]), LS.data_ptr(), ldq, nq, kc, None, samp_sid.data_ptr(),
-                                                 samp_val.data_ptr(), ws["scratch"].data_ptr(), st), "cw_dense_paths_topk (sample)")
-            sv = samp_val.view(-1)[: nq * kc].view(nq, kc)
-            ss = samp_sid.view(-1)[: nq * kc].view(nq, kc)
-            tau = torch.where(ss[:, kc - 1] >= 0, sv[:, kc - 1], tau)
-        ws["f_cnt"][:nq].zero_()
-        _lib.check(L.cw_tc_score_tiles(C.byref(tx_leaf), ws["xt"].data_ptr(), nq, 2, fx["n_s"], tx_leaf.n_ntiles - fx["n_s"], None,
-                                       ldq, S.data_ptr(), fx["leaf_rec"].data_ptr(), fx["n_leaf"], tau.data_ptr(), cap,
-                                       ws["f_cnt"].data_ptr(), ws["f_val"].data_ptr(), ws["f_row"].data_ptr(), st),
-                   "cw_tc_score_tiles (filter)")
-        _lib.check(L.cw_tc_select(nq, kc, samp_sid.data_ptr() if samp_sid is not None else None,
-                                  samp_val.data_ptr() if samp_val is not None else None, cap, ws["f_cnt"].data_ptr(),
-                                  ws["f_val"].data_ptr(), ws["f_row"].data_ptr(), fx["sent_off"].data_ptr(),
-                                  fx["sent_ids"].data_ptr(), ws["cand_sid"].data_ptr(), ws["cand_val"].data_ptr(),
-                                  ws["f_ovf"].data_ptr(), st), "cw_tc_select")
-        return ws["f_ovf"][:nq]
-
-    def _node_scores_call(self, q, nq, ws):
-        L = _lib.load()
-        if self.mode in ("tf32x3", "tf32x3f"):
-            _lib.check(L.cw_dense_node_scores_tc(C.byref(self.tx), q.data_ptr(), nq, ws["xt"].data_ptr(),
-                                                 ws["scores"].data_ptr(), ws["ldq"], _lib.stream_ptr()), "cw_dense_node_scores_tc")
-        else:
-            _lib.check(L.cw_dense_node_scores(C.byref(self.ix), q.data_ptr(), nq, ws["xt"].data_ptr(),
-                                              ws["scores"].data_ptr(), ws["ldq"], _lib.stream_ptr()), "cw_dense_node_scores")
+        fi = _lib.CwFusedIndex()
+        fi.ix = self.ix
+        fi.n_int, fi.n_leaf, fi.n_sample_tiles = n_int, n_leaf, hx["n_s"]
+        if n_int:
+            hx["int_rows"] = i32(F["int_rows"])
+            fi.internal, hx["B_int"], hx["rc_int"] = hset(hx["int_rows"], n_int, _lib.H_F2, 3, None)
+            hx["int_parent"], hx["int_w"], hx["level_off"] = i32(F["int_parent"]), f32(F["int_w"]), i32(F["level_off"])
+            fi.int_parent, fi.int_w, fi.level_off = hx["int_parent"].data_ptr(), hx["int_w"].data_ptr(), hx["level_off"].data_ptr()
+            fi.n_levels = len(F["level_off"]) - 1
+        hx["leaf_aux"] = [f32(F["leaf_w"]), f32(F["leaf_inv_len"]), i32(F["leaf_parent"]), i32(F["leaf_len"])]
+        fi.leaves, hx["B_leaf"], hx["rc_leaf"] = hset(hx["leaf_rows"], n_leaf, hx["leaf_layout"], 1, hx["leaf_aux"])
+        hx["leaf_pos"] = i32(np.searchsorted(self._pos_leaf_row, F["leaf_rows"]))
+        hx["sent_off"], hx["sent_ids"] = i32(F["sent_off"]), i32(F["sent_ids"])
+        fi.leaf_row_b, fi.leaf_pos = hx["leaf_rows"].data_ptr(), hx["leaf_pos"].data_ptr()
+        fi.sent_off, fi.sent_ids = hx["sent_off"].data_ptr(), hx["sent_ids"].data_ptr()
+        # row-major {r, mb} rows: the operands of the exact arithmetic in the finish kernel
+        hx["rows"] = torch.empty((self.nn, d, 2), dtype=torch.float32, device=dev)
+        _lib.check(L.cw_index_rows_build(store, self.order.data_ptr(), self.nn, hx["rows"].data_ptr(), st),
+                   "cw_index_rows_build")
+        fi.rows = hx["rows"].data_ptr()
+        # constants of eps: hmax = max_b sum_d mean^2/var (= sum_d mb^2), lmax = max_b |sumlog|,
+        # wfac = max over path lengths of sum_j |level_w[j]| / len; e1max = largest rounding-error coefficient of a leaf
+        hmax = 0.0
+        for lo in range(0, self.nn, 65536):
+            hmax = max(hmax, float(hx["rows"][lo:lo + 65536, :, 1].double().square().sum(1).max()))
+        fi.hmax = hmax * (1.0 + 1e-6) + 1e-6
+        fi.lmax = float(self.sumlog[: self.nn].abs().max())
+        cw = np.cumsum(np.abs(self._level_w_host))
+        fi.wfac = float(max(1.0, (cw[self._path_lens - 1] / self._path_lens).max()))
+        fi.e1max = float(hx["rc_leaf"].view(-1, 8)[:n_leaf, 4].max())
+        fi.eps_scale = self.eps_scale
+        fi.prior_var = float(self.tree.prior_var.item())
+        torch.cuda.current_stream().synchronize()
+        hx["fi"] = fi
+        hx["smem_ok"] = self.max_len <= 512
+        self.hx = hx
 
     def bytes(self):
         b = (self.R.numel() + self.MB.numel() + self.sumlog.numel()) * 4
-        if self.tx is not None:
-            b += self.tcB.numel() + self.hconst.numel() * 4 + self.rows.numel() * 4
+        if self.hx is not None:
+            b += sum(self.hx[n].numel() * self.hx[n].element_size() for n in ("B_int", "rc_int", "B_leaf", "rc_leaf", "rows")
+                     if n in self.hx)
         return b
 
+    # ------------------------------------------------------------------ work buffers
     def chunk_queries(self):
         return int(max(256, min(65535, self.SCORE_BUDGET_BYTES // (self.ld * 4)) // 256 * 256))  # whole 256-query tiles
 
     def workspace(self, nq, k):
-        """Device work buffers for chunks of up to nq queries and top-k up to k (grown on demand)."""
+        """Device work buffers of the FP32 form for chunks of up to nq queries and top-k up to k (grown on demand)."""
         ws = self._ws
         if ws and ws["cap_q"] >= nq and ws["cap_k"] >= k:
             return ws
@@ -281,183 +209,211 @@ class DenseIndex:
         nq = max(nq, ws["cap_q"]) if ws else nq
         k = max(k, ws["cap_k"], 1) if ws else max(k, 1)
         self._ws = ws = None
+        ldq = int(L.cw_score_ldq(nq))
         ws = dict(
-            cap_q=nq, cap_k=k,
+            cap_q=nq, cap_k=k, ldq=ldq,
             q=torch.empty((nq, self.tree.d), dtype=torch.float32, device=dev),
-            # query operands: k-major tiles (FP32 kernel) or swizzled hi/lo images (tensor-core kernel)
-            xt=torch.empty(max(L.cw_xt_floats(nq, self.tree.d) * 4, L.cw_tc_a_bytes(nq, self.tree.d)), dtype=torch.uint8,
-                           device=dev),
-            ldq=int(L.cw_score_ldq(nq)),
-            scores=torch.empty((self.ld, int(L.cw_score_ldq(nq))), dtype=torch.float32, device=dev),  # node-major
+            xt=torch.empty(L.cw_xt_floats(nq, self.tree.d), dtype=torch.float32, device=dev),  # k-major query tiles
+            scores=torch.empty((self.ld, ldq), dtype=torch.float32, device=dev),  # node-major
             sid=torch.empty((nq, k), dtype=torch.int32, device=dev),
             val=torch.empty((nq, k), dtype=torch.float32, device=dev),
+            scratch=torch.empty(max(1, nq * L.cw_topk_chunks(max(self.n_pos, 1)) * k * 2), dtype=torch.int32, device=dev),
         )
-        c0 = self.candidates(k)
-        kc = max(k, c0, 32 if c0 else 0, self.candidates(k, 1))  # 32: room for the adaptive first level
-        ws["scratch"] = torch.empty(max(1, nq * L.cw_topk_chunks(max(self.n_pos, 1)) * kc * 2), dtype=torch.int32, device=dev)
-        ws["cand_sid"] = torch.empty((nq, kc), dtype=torch.int32, device=dev)
-        ws["cand_val"] = torch.empty((nq, kc), dtype=torch.float32, device=dev)
-        ws["fail"] = torch.zeros(1 + nq, dtype=torch.int32, device=dev)
         self._ws = ws
         return ws
 
-    def candidates(self, k, level=0):
-        """Candidates per query the tensor-core pre-filter hands to the exact re-score: level 0 = first attempt,
-        level 1 = second attempt for the queries the first one flagged (0 = no such level: this k is served by the
-        FP32 path -- k too large, or paths too long for the re-score kernel's shared memory)."""
-        if k < 1 or k > 32 or not self.n_pos or level > 1:
-            return 0
-        # enough that the weakest candidate sits below (k-th best) - 2 eps for (nearly) every query: the first level
-        # starts at 24 (k <= 10: at cfg3 and cfg4 the gap between ranks 10 and 24 exceeds the margin for all but
-        # ~1 query in 10^4, tools/tc_gap_probe.py; 16 would save 0.9 ms of path kernel per 10k queries but the
-        # second pass for its 0.1 % flagged queries costs more) and is raised by _adapt() when more than 0.5 % of
-        # a batch had to be escalated; lists up to 32 use the fast insertion path
-        kc = min(max(self._kc0, k + 6), 32) if k <= 16 else 2 * k
-        if level == 1:
-            if kc >= _lib.RESCORE_MAX_KC:
-                return 0
-            kc = _lib.RESCORE_MAX_KC
-        if kc * self.max_len > 65535 or _lib.load().cw_rescore_smem_bytes(self.tree.d, self.max_len, kc) > 200 * 1024:
-            return 0
-        return kc
+    def small_workspace(self, k):
+        """Buffers of the exact small-batch path (cw_small_predict)."""
+        sm = self._sm
+        if sm and sm["cap_k"] >= k:
+            return sm
+        L, dev, Q = _lib.load(), self.tree.device, _lib.SMALL_Q
+        k = max(k, sm["cap_k"]) if sm else max(k, 10)
+        self._sm = sm = dict(
+            cap_k=k,
+            Q=torch.empty((Q, self.tree.d), dtype=torch.float32, device=dev),
+            scores=torch.empty((self.ld, Q), dtype=torch.float32, device=dev),
+            scratch=torch.empty(L.cw_small_scratch_words(max(self.n_pos, 1), k), dtype=torch.int32, device=dev),
+            sid=torch.empty((Q, k), dtype=torch.int32, device=dev),
+            val=torch.empty((Q, k), dtype=torch.float32, device=dev),
+            n=torch.zeros(1, dtype=torch.int32, device=dev),
+            sid_host=torch.empty((Q, k), dtype=torch.int32).pin_memory(),
+            val_host=torch.empty((Q, k), dtype=torch.float32).pin_memory(),
+        )
+        return sm
 
-    def _work_struct(self, ws, k):
-        w = _lib.CwDenseWork()
-        w.Q_dev, w.xt_scratch, w.node_scores, w.ldq = ws["q"].data_ptr(), ws["xt"].data_ptr(), ws["scores"].data_ptr(), ws["ldq"]
-        w.out_sid_dev, w.out_score_dev, w.scratch = ws["sid"].data_ptr(), ws["val"].data_ptr(), ws["scratch"].data_ptr()
-        w.cand_sid, w.cand_score, w.fail = ws["cand_sid"].data_ptr(), ws["cand_val"].data_ptr(), ws["fail"].data_ptr()
-        w.kc, w.kc2 = self.candidates(k), self.candidates(k, 1)
-        return w
+    def fused_chunk_queries(self):
+        n_int_pad = (self.hx["n_int"] + _lib.H_TILE - 1) // _lib.H_TILE * _lib.H_TILE
+        return int(max(256, min(32768, self.SCORE_BUDGET_BYTES // (max(n_int_pad, 1) * 4)) // 256 * 256))
 
+    def fused_workspace(self, nq, k):
+        """cw_fused_work for chunks of up to nq queries (rounded to whole tiles, at most fused_chunk_queries())."""
+        L, dev, d, hx = _lib.load(), self.tree.device, self.tree.d, self.hx
+        cap_q = min((max(nq, 1) + _lib.H_TILE - 1) // _lib.H_TILE * _lib.H_TILE, self.fused_chunk_queries())
+        sm = self.small_workspace(k)
+        hw = self._hws
+        if hw and hw["cap_q"] >= cap_q and hw["cap_k"] >= k and hw["sm"] is sm:
+            return hw
+        self._hws = hw = None
+        n_int_pad = (hx["n_int"] + _lib.H_TILE - 1) // _lib.H_TILE * _lib.H_TILE
+        cap = self.FUSED_CAP
+        hw = dict(
+            cap_q=cap_q, cap_k=k, sm=sm,
+            Q=torch.empty((cap_q, d), dtype=torch.float32, device=dev),
+            A_int=torch.empty(max(16, L.cw_h_a_bytes(cap_q, d, _lib.H_F2, 3) if hx["n_int"] else 16), dtype=torch.uint8, device=dev),
+            A_leaf=torch.empty(L.cw_h_a_bytes(cap_q, d, hx["leaf_layout"], 1), dtype=torch.uint8, device=dev),
+            qv=torch.empty((cap_q, 4), dtype=torch.float32, device=dev),
+            S=torch.empty((max(n_int_pad, 1), cap_q), dtype=torch.float32, device=dev),
+            slots=torch.empty((cap_q, 32), dtype=torch.int32, device=dev),
+            tau=torch.empty(cap_q, dtype=torch.float32, device=dev),
+            cnt=torch.zeros(cap_q, dtype=torch.int32, device=dev),
+            cand_val=torch.empty((cap_q, cap), dtype=torch.float32, device=dev),
+            cand_row=torch.empty((cap_q, cap), dtype=torch.int32, device=dev),
+            flag=torch.zeros(4 + cap_q + _lib.SMALL_Q, dtype=torch.int32, device=dev),
+            sid=torch.empty((cap_q, k), dtype=torch.int32, device=dev),
+            val=torch.empty((cap_q, k), dtype=torch.float32, device=dev),
+            stats=torch.zeros(_lib.FUSED_STATS, dtype=torch.int32, device=dev),
+            stats_host=torch.zeros(_lib.FUSED_STATS, dtype=torch.int32).pin_memory(),
+        )
+        w = _lib.CwFusedWork()
+        w.cap_q, w.ldq, w.cap = cap_q, cap_q, cap
+        w.Q_dev, w.A_int, w.A_leaf, w.qv, w.S = (hw[n].data_ptr() for n in ("Q", "A_int", "A_leaf", "qv", "S"))
+        w.slots, w.tau, w.cnt, w.cand_val, w.cand_row = (hw[n].data_ptr() for n in ("slots", "tau", "cnt", "cand_val", "cand_row"))
+        w.flag, w.out_sid_dev, w.out_val_dev, w.stats = (hw[n].data_ptr() for n in ("flag", "sid", "val", "stats"))
+        w.sm_Q, w.sm_scores, w.sm_scratch = sm["Q"].data_ptr(), sm["scores"].data_ptr(), sm["scratch"].data_ptr()
+        w.sm_sid, w.sm_val, w.sm_n = sm["sid"].data_ptr(), sm["val"].data_ptr(), sm["n"].data_ptr()
+        hw["w"] = w
+        self._hws = hw
+        return hw
+
+    def _fused_struct(self, hw):
+        """The work struct with this call's audit settings; the index struct with the current eps."""
+        w, fi = hw["w"], self.hx["fi"]
+        w.audit_every = int(self.audit_every)
+        w.audit_phase = self._audit_phase
+        self._audit_phase += 1
+        fi.eps_scale = self.eps_scale
+        return fi, w
+
+    def _account(self, st):
+        """Fold the counters of one fused call (CW_FUSED_STATS words) into self.stats; an audit mismatch means the
+        statistical part of eps did not hold: widen it and say so."""
+        s = self.stats
+        s["flagged"] += int(st[0]); s["unresolved"] += int(st[1]); s["cand_overflow"] += int(st[2])
+        s["line_fail"] += int(st[3]); s["list_overflow"] += int(st[4]); s["queries"] += int(st[5])
+        s["candidates"] += int(np.asarray(st[6:8], np.int32).view(np.uint64)[0])
+        s["audited"] += int(st[8]); s["audit_mismatch"] += int(st[9])
+        if int(st[9]):
+            self.eps_scale *= 4.0
+            import warnings
+            warnings.warn(f"cobweb-b200: {int(st[9])} audited quer(ies) differed from the exact path; eps widened to "
+                          f"{self.eps_scale:.3g} (DenseIndex.stats['audit_mismatch'])")
+
+    # ------------------------------------------------------------------ predict
     def node_scores(self, Q):
-        """[nq, nn] node log-likelihood scores in index (BFS) order (CobwebWrapper.py:283-287)."""
+        """[nq, nn] node log-likelihood scores in index (BFS) order (CobwebWrapper.py:283-287), FP32 form."""
         nq = Q.shape[0]
         ws = self.workspace(nq, 0)
-        self._node_scores_call(Q, nq, ws)
+        _lib.check(_lib.load().cw_dense_node_scores(C.byref(self.ix), Q.data_ptr(), nq, ws["xt"].data_ptr(),
+                                                    ws["scores"].data_ptr(), ws["ldq"], _lib.stream_ptr()), "cw_dense_node_scores")
         return ws["scores"][: self.nn, :nq].T
 
-    def predict(self, Q, k, want_leaf_scores=False, mode=None, _level=0):
-        """Device batch -> (sids [nq,k] int32, scores [nq,k], leaf_scores [nq,L] or None).  mode overrides
-        self.mode for this call.  In "tf32x3" mode top-k goes pre-filter -> exact re-score; flagged queries are
-        answered again with more candidates (self.n_escalated) and what is still flagged on the FP32 pipe
-        (self.n_fallback); leaf_scores, if requested, come from the same node scores as the top-k of that mode
-        (approximate for "tf32x3")."""
+    def predict_small(self, Q, k):
+        """Exact small-batch path for up to SMALL_Q queries on the device (cw_small_predict)."""
+        nq = Q.shape[0]
+        sm = self.small_workspace(k)
+        sids = torch.empty((nq, k), dtype=torch.int32, device=Q.device)
+        vals = torch.empty((nq, k), dtype=torch.float32, device=Q.device)
+        _lib.check(_lib.load().cw_small_predict(C.byref(self.ix), Q.data_ptr(), nq, None, None, 0, 0, k, sm["Q"].data_ptr(),
+                                                sm["scores"].data_ptr(), sm["scratch"].data_ptr(), sm["sid"].data_ptr(),
+                                                sm["val"].data_ptr(), sm["n"].data_ptr(), sids.data_ptr(), vals.data_ptr(),
+                                                _lib.stream_ptr()), "cw_small_predict")
+        return sids, vals
+
+    def predict(self, Q, k, want_leaf_scores=False, mode=None, small=True):
+        """Device batch -> (sids [nq,k] int32, scores [nq,k], leaf_scores [nq,L] or None).  mode overrides self.mode for
+        this call; small=False keeps batches of up to SMALL_Q queries off the small-batch path (tests)."""
         L = _lib.load()
         if want_leaf_scores and self.sentence_ids is not None:
             raise ValueError("leaf scores are indexed by global sentence id; not available on a sentence shard")
         mode = mode or self.mode
-        if mode != self.mode:
-            prev = self.mode
-            self.set_mode(mode)
-            try:
-                return self.predict(Q, k, want_leaf_scores)
-            finally:
-                self.mode = prev
-        tensor = mode in ("tf32x3", "tf32x3f")
-        if tensor and k > 0 and not want_leaf_scores and self.nn < self.TENSOR_MIN_NODES:
-            return self.predict(Q, k, mode="fp32")  # launch-bound at this size: the FP32 path is the shorter one
-        kc = self.candidates(k, _level) if (tensor and not want_leaf_scores) else 0
-        if tensor and kc == 0 and k > 0 and not want_leaf_scores:
-            return self.predict(Q, k, mode="fp32")  # this k / depth is not served by the re-score kernel
-        # small batches: the fused pipeline's extra launches (one per tree level) cost more than the path kernel saves
-        fused = (mode == "tf32x3f" and kc > 0 and _level == 0 and getattr(self, "fx", None) is not None and
-                 Q.shape[0] >= self.FUSED_MIN_QUERIES)
-        if fused and self.fx["n_s"] == 0 and self.fx["n_leaf"] > self.FUSED_CAP:
-            fused = False  # too few leaf tiles to sample a threshold from, too many leaves for the candidate buffer
+        if mode not in self.MODES:
+            raise ValueError(f"mode must be one of {self.MODES}")
         nq_total = Q.shape[0]
+        if mode == "fused" and self.hx is None and self.n_pos:
+            self._build_fused()
+        if small and not want_leaf_scores and 1 <= k <= _lib.MAX_K and 0 < nq_total <= _lib.SMALL_Q and self.n_pos:
+            s, v = self.predict_small(Q, k)
+            return s, v, None
+        if mode == "fused" and not want_leaf_scores and self.hx is not None and 1 <= k <= _lib.FUSED_MAX_K and \
+                self.nn >= self.TENSOR_MIN_NODES and self.hx["smem_ok"] and nq_total > 0:
+            hw = self.fused_workspace(nq_total, k)
+            fi, w = self._fused_struct(hw)
+            sids = torch.empty((nq_total, k), dtype=torch.int32, device=Q.device)
+            vals = torch.empty((nq_total, k), dtype=torch.float32, device=Q.device)
+            hw["stats"].zero_()
+            _lib.check(L.cw_fused_predict(C.byref(fi), C.byref(w), Q.data_ptr(), nq_total, k, sids.data_ptr(), vals.data_ptr(),
+                                          _lib.stream_ptr()), "cw_fused_predict")
+            hw["stats_host"].copy_(hw["stats"], non_blocking=True)
+            torch.cuda.current_stream().synchronize()  # the one read-back of a call: counters (flagged / audit)
+            st = hw["stats_host"].numpy().copy()
+            self._account(st)
+            if st[1]:  # more flagged queries in a chunk than the device-side rounds take: the FP32 form answers them
+                idx = torch.nonzero(sids[:, 0] == _lib.SID_UNRESOLVED).view(-1)
+                s2, v2, _ = self.predict(Q[idx].contiguous(), k, mode="fp32", small=False)
+                sids[idx], vals[idx] = s2, v2
+            return sids, vals, None
         step = self.chunk_queries()
         sids = torch.empty((nq_total, max(k, 1)), dtype=torch.int32, device=Q.device)
         vals = torch.empty((nq_total, max(k, 1)), dtype=torch.float32, device=Q.device)
         leaf = torch.empty((nq_total, self.n_pos), dtype=torch.float32, device=Q.device) if want_leaf_scores else None
-        redo = []
         for lo in range(0, nq_total, step):
             nq = min(step, nq_total - lo)
             ws = self.workspace(min(step, nq_total), k)
             q = Q[lo:lo + nq]
-            ovf = None
-            if fused:
-                ovf = self._fused_candidates(q, nq, kc, ws)
-            else:
-                self._node_scores_call(q, nq, ws)
-            if kc:
-                if not fused:
-                    _lib.check(L.cw_dense_paths_topk(C.byref(self.ix), ws["scores"].data_ptr(), ws["ldq"], nq, kc, None,
-                                                     ws["cand_sid"].data_ptr(), ws["cand_val"].data_ptr(),
-                                                     ws["scratch"].data_ptr(), _lib.stream_ptr()), "cw_dense_paths_topk")
-                tx = self.tx
-                _lib.check(L.cw_dense_rescore(self.tree.store.struct(), C.byref(self.ix), tx.rows, tx.pos_of_sid, q.data_ptr(),
-                                              nq, kc, ws["cand_sid"].data_ptr(), ws["cand_val"].data_ptr(), k, tx.hmax, tx.lmax,
-                                              tx.wfac, tx.eps_scale, sids[lo:lo + nq].data_ptr(), vals[lo:lo + nq].data_ptr(),
-                                              ws["fail"].data_ptr(), _lib.stream_ptr()), "cw_dense_rescore")
-                nf = int(ws["fail"][0])  # one 4-byte read-back per chunk
-                flagged = ws["fail"][1:1 + nf].long()
-                if ovf is not None and bool(ovf.any()):  # candidate buffer overflow: treat like a flagged query
-                    flagged = torch.unique(torch.cat([flagged, torch.nonzero(ovf).view(-1)]))
-                if flagged.numel():
-                    redo.append(flagged + lo)
-            else:
-                _lib.check(L.cw_dense_paths_topk(C.byref(self.ix), ws["scores"].data_ptr(), ws["ldq"], nq, k,
-                                                 leaf[lo:lo + nq].data_ptr() if leaf is not None else None,
-                                                 sids[lo:lo + nq].data_ptr(), vals[lo:lo + nq].data_ptr(),
-                                                 ws["scratch"].data_ptr(), _lib.stream_ptr()), "cw_dense_paths_topk")
-        if kc and _level == 0:
-            self._adapt(nq_total, sum(int(r.numel()) for r in redo))
-        if redo:
-            idx = torch.cat(redo)
-            if self.candidates(k, _level + 1):
-                self.n_escalated += int(idx.numel())
-                s2, v2, _ = self.predict(Q[idx].contiguous(), k, mode="tf32x3" if fused else None, _level=_level + 1)
-            else:
-                self.n_fallback += int(idx.numel())
-                s2, v2, _ = self.predict(Q[idx].contiguous(), k, mode="fp32")
-            sids[idx], vals[idx] = s2, v2
+            _lib.check(L.cw_dense_node_scores(C.byref(self.ix), q.data_ptr(), nq, ws["xt"].data_ptr(), ws["scores"].data_ptr(),
+                                              ws["ldq"], _lib.stream_ptr()), "cw_dense_node_scores")
+            _lib.check(L.cw_dense_paths_topk(C.byref(self.ix), ws["scores"].data_ptr(), ws["ldq"], nq, k,
+                                             leaf[lo:lo + nq].data_ptr() if leaf is not None else None,
+                                             sids[lo:lo + nq].data_ptr(), vals[lo:lo + nq].data_ptr(),
+                                             ws["scratch"].data_ptr(), _lib.stream_ptr()), "cw_dense_paths_topk")
         return sids, vals, leaf
 
-    _kc0 = 24        # first-level candidates per query (k <= 16), adapted to the escalation rate
-
-    def _adapt(self, n_queries, n_flagged):
-        if n_queries >= 64 and n_flagged > 0.005 * n_queries and self._kc0 < 32:
-            self._kc0 += 8
-
-    n_escalated = 0  # queries whose first candidate list could not be decided and were re-run with more candidates
-    n_fallback = 0   # queries answered by the FP32 path because the re-score margin did not hold at any level
-
     def predict_host(self, Q_host, k, out_sid=None, out_val=None):
-        """Host batch (numpy / pinned tensor) -> host ids/scores through the single C-ABI call
-        cw_predict_dense_host (H2D + kernels + D2H + sync inside)."""
+        """Host batch (numpy / pinned tensor) -> host ids/scores through ONE C-ABI call per batch:
+        cw_fused_predict_host ("fused" mode), cw_small_predict_host (up to SMALL_Q queries) or cw_predict_dense_host
+        (FP32 form); H2D + kernels + D2H + sync inside."""
         L = _lib.load()
         Qh = Q_host if torch.is_tensor(Q_host) else torch.from_numpy(np.ascontiguousarray(Q_host, np.float32))
         nq_total = Qh.shape[0]
-        step = self.chunk_queries()
         if out_sid is None:
             out_sid = torch.empty((nq_total, k), dtype=torch.int32)
             out_val = torch.empty((nq_total, k), dtype=torch.float32)
-        if self.mode == "tf32x3f" and self.candidates(k) > 0 and self.nn >= self.TENSOR_MIN_NODES:
-            # fused mode: pinned host batch -> device, the device pipeline, ids/scores back (no single C call yet)
-            for lo in range(0, nq_total, step):
-                nq = min(step, nq_total - lo)
-                ws = self.workspace(min(step, nq_total), k)
-                qd = ws["q"][:nq]
-                qd.copy_(Qh[lo:lo + nq], non_blocking=True)
-                sd, vd, _ = self.predict(qd, k)
-                out_sid[lo:lo + nq].copy_(sd, non_blocking=True)
-                out_val[lo:lo + nq].copy_(vd, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+        if 0 < nq_total <= _lib.SMALL_Q and 1 <= k <= _lib.MAX_K and self.n_pos:
+            sm = self.small_workspace(k)
+            _lib.check(L.cw_small_predict_host(C.byref(self.ix), Qh.data_ptr(), nq_total, k, sm["Q"].data_ptr(),
+                                               sm["scores"].data_ptr(), sm["scratch"].data_ptr(), sm["sid"].data_ptr(),
+                                               sm["val"].data_ptr(), sm["n"].data_ptr(), out_sid.data_ptr(), out_val.data_ptr(),
+                                               _lib.stream_ptr()), "cw_small_predict_host")
             return out_sid, out_val
-        tensor = self.mode in ("tf32x3", "tf32x3f") and self.candidates(k) > 0 and self.nn >= self.TENSOR_MIN_NODES
-        nfb = (C.c_int32 * 2)(0, 0)
+        if self.fused_ready(k) and nq_total > 0:
+            hw = self.fused_workspace(nq_total, k)
+            fi, w = self._fused_struct(hw)
+            st = (C.c_int32 * _lib.FUSED_STATS)()
+            _lib.check(L.cw_fused_predict_host(C.byref(fi), C.byref(w), Qh.data_ptr(), nq_total, k, out_sid.data_ptr(),
+                                               out_val.data_ptr(), st, _lib.stream_ptr()), "cw_fused_predict_host")
+            self._account(np.asarray(list(st), np.int32))
+            return out_sid, out_val
+        step = self.chunk_queries()
         for lo in range(0, nq_total, step):
             nq = min(step, nq_total - lo)
             ws = self.workspace(min(step, nq_total), k)
-            w = self._work_struct(ws, k)
-            _lib.check(L.cw_predict_dense_host(C.byref(self.ix), C.byref(self.tx) if tensor else None,
-                                               self.tree.store.struct(), Qh[lo:lo + nq].data_ptr(), nq, k, C.byref(w),
-                                               out_sid[lo:lo + nq].data_ptr(), out_val[lo:lo + nq].data_ptr(), nfb,
+            w = _lib.CwDenseWork()
+            w.Q_dev, w.xt_scratch, w.node_scores, w.ldq = ws["q"].data_ptr(), ws["xt"].data_ptr(), ws["scores"].data_ptr(), ws["ldq"]
+            w.out_sid_dev, w.out_score_dev, w.scratch = ws["sid"].data_ptr(), ws["val"].data_ptr(), ws["scratch"].data_ptr()
+            _lib.check(L.cw_predict_dense_host(C.byref(self.ix), C.byref(w), Qh[lo:lo + nq].data_ptr(), nq, k,
+                                               out_sid[lo:lo + nq].data_ptr(), out_val[lo:lo + nq].data_ptr(),
                                                _lib.stream_ptr()), "cw_predict_dense_host")
-            self.n_escalated += nfb[0]
-            self.n_fallback += nfb[1]
-            if tensor:
-                self._adapt(nq, nfb[0])
         return out_sid, out_val
 
 
@@ -531,12 +487,24 @@ class CobwebWrapper:
             if new_embeddings.shape[1] != self.tree.shape[0]:
                 print(f"[Warning] Provided vector dim {new_embeddings.shape[1]} != tree dim {self.tree.shape[0]}, re-encoding...")
                 new_embeddings = self.encode_func(new_sentences)
-        n = len(new_sentences)
-        X = self.tree._as_device_mat(new_embeddings)[:n]
-        leaves = self.tree.ifit_batch(X, tag_sentences=True)
+        X = self.tree._as_device_mat(new_embeddings)
+        n = min(len(new_sentences), X.shape[0])  # the reference zips sentences with embeddings (CobwebWrapper.py:70)
+        new_sentences = list(new_sentences[:n])
+        try:
+            leaves = self.tree.ifit_batch(X[:n], tag_sentences=True).cpu().numpy()
+        except _lib.CobwebB200Error as e:
+            # rows inserted before the failure stay in the tree (their n_sent is tagged): keep wrapper and tree consistent
+            done = int(getattr(e, "completed", 0))
+            if done:
+                self._record(new_sentences[:done], e.leaves[:done].cpu().numpy())
+            raise
+        self._record(new_sentences, leaves)
+
+    def _record(self, new_sentences, leaves):
         self.sentences.extend(new_sentences)
-        self._leaf_of_sentence = np.concatenate([self._leaf_of_sentence, leaves.cpu().numpy()])
-        self.tree._sent = {}
+        self._leaf_of_sentence = np.concatenate([self._leaf_of_sentence, np.asarray(leaves, np.int32)])
+        self.tree._sent_stale = True   # node.sentence_id lists are rebuilt from the id map on next access
+        self.tree._sent_loader = self._load_sentence_lists
         self._invalidate_prediction_index()
 
     @property
@@ -544,12 +512,19 @@ class CobwebWrapper:
         """sentence id -> concept handle (CobwebWrapper.py:77)."""
         return {i: CobwebNode(self.tree, int(n)) for i, n in enumerate(self._leaf_of_sentence)}
 
-    def _sync_sentence_lists(self):
-        if self.tree._sent:
-            return
+    def _load_sentence_lists(self):
+        """leaf -> [sentence ids] from the id map (leaf.sentence_id.append of CobwebWrapper.py:73-77, done lazily)."""
+        from .tree import SentenceList
+        sent = {}
         order = np.argsort(self._leaf_of_sentence, kind="stable")
         for sid in order:
-            self.tree._sent.setdefault(int(self._leaf_of_sentence[sid]), []).append(int(sid))
+            nid = int(self._leaf_of_sentence[sid])
+            if nid >= 0:
+                sent.setdefault(nid, SentenceList(self.tree, nid)).extend([int(sid)])
+        return sent
+
+    def _sync_sentence_lists(self):
+        self.tree._sync_sentences()
 
     def _invalidate_prediction_index(self):
         self._index = None
@@ -568,21 +543,20 @@ class CobwebWrapper:
         self._index = ix.set_mode(self._resolve_mode(ix))
         self.max_depth = max(self.max_depth, self._index.max_depth)
 
-    # Scoring mode of the dense index (DenseIndex.MODES; every mode returns the same ids and scores).  "auto": the
-    # fused tensor-core mode for indexes of AUTO_TENSOR_NODES nodes and more -- it builds two more operand copies, which
-    # 180 GB of HBM is there for -- and the FP32 pipe below (launch-bound at that size).
+    # Mode of the dense index (DenseIndex.MODES; both return the same ids and scores).  "auto": the fused tcgen05
+    # pipeline for indexes of AUTO_TENSOR_NODES nodes and more -- it builds fp16 operand copies, which 180 GB of HBM
+    # is there for -- and the FP32 pipe below (launch-bound at that size).
     dense_mode = os.environ.get("COBWEB_B200_DENSE_MODE", "auto")
-    AUTO_TENSOR_NODES = 16384
+    AUTO_TENSOR_NODES = DenseIndex.TENSOR_MIN_NODES
 
     def _resolve_mode(self, index):
         if self.dense_mode != "auto":
             return self.dense_mode
-        return "tf32x3f" if index.nn >= self.AUTO_TENSOR_NODES else "fp32"
+        return "fused" if index.nn >= self.AUTO_TENSOR_NODES else "fp32"
 
     def set_dense_mode(self, mode):
-        """Additive: where cobweb_predict_fast / predict_fast_batch compute node scores -- "auto" (default), "fp32"
-        (FP32 pipe), "tf32x3" (tcgen05 tensor cores, split-TF32 operands), "tf32x3f" (the same, fused).  See
-        DenseIndex.MODES."""
+        """Additive: how cobweb_predict_fast / predict_fast_batch compute the top-k -- "auto" (default), "fp32" (FP32
+        pipe) or "fused" (tcgen05 fp16 filter + exact re-score).  See DenseIndex.MODES."""
         if mode != "auto" and mode not in DenseIndex.MODES:
             raise ValueError(f"mode must be 'auto' or one of {DenseIndex.MODES}")
         self.dense_mode = mode

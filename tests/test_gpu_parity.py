@@ -295,13 +295,14 @@ def test_properties_at_scale():
     assert np.mean([i in g for i, g in enumerate(ids.cpu().numpy())]) > 0.99  # a document retrieves itself
     # the tensor-core path at this size (several node tiles per SM, whitened operands = the cancellation-heavy case):
     # same ids, same scores, on a batch that is not a multiple of any tile
-    w.set_dense_mode("tf32x3")
+    w.set_dense_mode("fused")
     qb, _ = synth.queries(x, 3001, "whitened", seed=2)
     ids_t, vals_t = w.predict_fast_batch(np.concatenate([q, qb]), 10)
     w.set_dense_mode("fp32")
     ids_f, vals_f = w.predict_fast_batch(np.concatenate([q, qb]), 10)
     assert torch.equal(ids_t, ids_f) and torch.equal(vals_t, vals_f)
-    assert torch.equal(ids_t[:512], ids) and w._index.n_fallback <= 8
+    st = w._index.stats
+    assert torch.equal(ids_t[:512], ids) and st["flagged"] <= 32 and st["audit_mismatch"] == 0 and st["queries"] == 3513, st
     # oracle cross-check on the engine-built tree: load it into the oracle, compare best-first on a sample
     mean, m2 = w.tree.store.rows(b["order"])
     ref = OracleTree(d)
@@ -375,7 +376,7 @@ def test_store_sharded_predict_matches_full():
         mi, mv = parallel.merge_topk(ci, cv, k)
         assert torch.equal(mi, full_i) and torch.equal(mv, full_v)
     # the same through the tensor-core modes (a shard index carries global sentence ids and its own row subset)
-    for mode in ("tf32x3", "tf32x3f"):
+    for mode in ("fused",):
         w.set_dense_mode(mode)
         w._shard_key = None
         parts = [w.predict_fast_sharded(q, k, world=2, rank=r) for r in range(2)]
@@ -481,52 +482,49 @@ def test_wrapper_input_conventions():
 
 
 @pytest.mark.parametrize("n,d,kind,k", [(700, 128, "unit", 10), (900, 256, "whitened", 5), (400, 1024, "unit", 10),
-                                        (300, 100, "unit", 3), (1500, 40, "whitened", 16), (600, 384, "unit", 32)])
-def test_tensor_core_predict_matches_fp32_path(n, d, kind, k):
-    """"tf32x3" dense predict (tcgen05 split-TF32 contraction -> top-kc candidates -> exact re-score,
-    cw_tensor.cu + cw_rescore.cu) returns the FP32-pipe path's ids AND scores bit for bit; its raw node
-    scores agree with the FP32 kernel and with the oracle (CobwebWrapper.py:283-287) far inside the 1e-4
-    relative bar of the contract."""
+                                        (300, 100, "unit", 3), (1500, 40, "whitened", 16), (600, 384, "unit", 30)])
+def test_fused_predict_matches_fp32_path(n, d, kind, k):
+    """"fused" dense predict (cw_half.cu: fp16x3 internal rows -> cumulative sums, one-product fp16 leaf filter with its
+    derived error bound, exact refine + re-score in the finish kernel) returns the FP32-pipe path's ids AND scores bit
+    for bit, through the device call, the one-call host entry and the reference-shaped API; the cumulative ancestor
+    sums it builds agree with the FP32 node scores far inside the 1e-4 relative bar of the contract."""
     x = synth.corpus(n, d, kind, seed=3)
     w = CobwebWrapper(corpus=[None] * n, corpus_embeddings=x)
-    q, _ = synth.queries(x, 333, kind, seed=4)  # not a multiple of the 128-query tile
+    q, _ = synth.queries(x, 333, kind, seed=4)  # not a multiple of the 256-query tile
     qd = torch.from_numpy(q).cuda()
     w.build_prediction_index()
     ix = w._index
     ns32 = ix.node_scores(qd).clone()
     ids32, v32, _ = ix.predict(qd, k)
-    ix.set_mode("tf32x3")
-    nstc = ix.node_scores(qd).clone()
-    # tolerance: 1e-5 of the score plus the cancellation floor of the contraction form (operand magnitude T)
-    x2 = float((qd * qd).sum(1).max())
-    floor = 2.0 ** -18 * 2.0 * (x2 / w.tree.store.prior_var + ix.tx.hmax)
-    err = (nstc - ns32).abs()
-    assert bool((err <= 1e-5 * ns32.abs() + floor).all()), float(err.max())
-    ref = OracleTree(d)
-    ref.ifit(x)
-    ref.build_index()
-    rns, _ = ref.dense_scores(q[:64])
-    np.testing.assert_allclose(nstc[:64].cpu().numpy(), rns, rtol=1e-5, atol=floor + 8 * EPS32 * float(np.abs(rns).max()))
-    assert k < ix.candidates(k) <= 64
-    before = ix.n_fallback
+    ix.set_mode("fused")
+    assert ix.fused_ready(k)
     ids, vals, _ = ix.predict(qd, k)
     assert torch.equal(ids, ids32) and torch.equal(vals, v32)
+    st = dict(ix.stats)
+    assert st["queries"] == 333 and st["audit_mismatch"] == 0 and st["audited"] >= 1 and st["unresolved"] == 0, st
+    assert st["flagged"] <= 4, st  # the line test holds for (nearly) every query on continuous data
+    # root row of the cumulative sums = the root's node score: fp16 split operands vs the FP32 kernel
+    F = ix.hx["F"]
+    root = ix._hws["S"][0, :333]
+    x2 = float((qd * qd).sum(1).max())
+    floor = 2.0 ** -18 * 2.0 * (x2 / w.tree.store.prior_var + ix.hx["fi"].hmax)
+    want = ns32[:, int(F["int_rows"][0])] * float(F["int_w"][0])
+    assert bool(((root - want).abs() <= 1e-5 * want.abs() + floor).all()), float((root - want).abs().max())
     hs, hv = ix.predict_host(q, k)
     assert np.array_equal(hs.numpy(), ids32.cpu().numpy()) and np.array_equal(hv.numpy(), v32.cpu().numpy())
-    assert ix.n_fallback - before <= 4  # the margin holds for (nearly) every query on continuous data
-    # reference-shaped API in tensor mode
-    w.set_dense_mode("tf32x3")
+    # reference-shaped API (one query: the exact small-batch path)
+    w.set_dense_mode("fused")
     assert w.cobweb_predict_fast(q[0], k=k, return_ids=True, is_embedding=True) == list(ids32[0].cpu().numpy())
 
 
-def test_tensor_core_predict_fallback_paths():
-    """Flagged queries (duplicates: more equal-scoring sentences than candidates), k beyond the re-score
-    kernel's range, fewer sentences than candidates, a level-weight schedule: always the FP32 path's answer."""
+def test_fused_predict_flagged_queries_and_fallbacks():
+    """Queries the device cannot decide (duplicates: more equal-scoring sentences than the finish kernel's lists hold), k
+    beyond the fused range, fewer sentences than k, a level-weight schedule: always the FP32 path's answer."""
     rng = np.random.default_rng(5)
     base = synth.corpus(40, 64, "unit", seed=6)
-    # leaves with 70, 70 and 40 identical sentences: more equal-scoring sentences than first-level (24) resp. second-level
-    # (64) candidates
-    x = np.concatenate([np.repeat(base[:2], 70, axis=0), np.repeat(base[2:3], 40, axis=0), base[3:]]).astype(np.float32)
+    # leaves with 150, 70 and 40 identical sentences: 150 > CW_FUSED_MAX_SENT
+    x = np.concatenate([np.repeat(base[:1], 150, axis=0), np.repeat(base[1:2], 70, axis=0), np.repeat(base[2:3], 40, axis=0),
+                        base[3:]]).astype(np.float32)
     x = x[rng.permutation(len(x))]
     w = CobwebWrapper(corpus=[None] * len(x), corpus_embeddings=x)
     q = np.concatenate([base[:3] + 1e-3, synth.queries(x, 61, "unit", seed=7)[0]]).astype(np.float32)
@@ -536,28 +534,59 @@ def test_tensor_core_predict_fallback_paths():
             w.set_level_weights(weights)
         w.build_prediction_index()
         ix = w._index
-        for k in (1, 10, 32, 40):
+        for k in (1, 10, 30, 40):
             ix.set_mode("fp32")
-            ids32, v32, _ = ix.predict(qd, k)
-            ix.set_mode("tf32x3")
+            ids32, v32, _ = ix.predict(qd, k, small=False)
+            ix.set_mode("fused")
             for call in ("device", "host"):
-                n0, e0 = ix.n_fallback, ix.n_escalated
+                f0 = ix.stats["flagged"]
                 if call == "device":
-                    ids, vals, _ = ix.predict(qd, k)
+                    ids, vals, _ = ix.predict(qd, k, small=False)
                     assert torch.equal(ids, ids32) and torch.equal(vals, v32), (k, weights)
                 else:
                     hs, hv = ix.predict_host(q, k)
                     assert np.array_equal(hs.numpy(), ids32.cpu().numpy()) and np.array_equal(hv.numpy(), v32.cpu().numpy()), k
                 if k == 10 and weights is None:
-                    # with the default weights a query next to a leaf ranks that leaf first: its 70 (resp. 40) equal-scoring
-                    # sentences cannot be decided from 24 candidates, the 70 not from 64 either
-                    assert ix.n_escalated - e0 >= 3 and ix.n_fallback - n0 >= 1, (call, ix.n_escalated - e0, ix.n_fallback - n0)
-    # fewer sentences than candidates
+                    # a query next to the 150-sentence leaf ranks it first: its sentences overflow the finish kernel's
+                    # list, the query is flagged and answered by the exact small-batch path on the device
+                    assert ix.stats["flagged"] - f0 >= 1 and ix.stats["unresolved"] == 0, ix.stats
+    assert ix.stats["audit_mismatch"] == 0
+    # fewer sentences than k
     w2 = CobwebWrapper(corpus=[None] * 12, corpus_embeddings=base[:12])
     w2.build_prediction_index()
-    a, b, _ = w2._index.predict(qd, 10)
-    c, e, _ = w2._index.set_mode("tf32x3").predict(qd, 10)
+    a, b, _ = w2._index.predict(qd, 20, small=False)
+    c, e, _ = w2._index.set_mode("fused").predict(qd, 20, small=False)
     assert torch.equal(a, c) and torch.equal(b, e)
+    # more flagged queries than the device-side rounds take (2 x 32): every query sits on the 150-sentence leaf
+    qq = np.repeat(base[:1], 200, axis=0) + 1e-3 * rng.standard_normal((200, 64)).astype(np.float32)
+    ix = w._index
+    ix.set_mode("fp32")
+    i32, f32v, _ = ix.predict(torch.from_numpy(qq).cuda(), 10, small=False)
+    ix.set_mode("fused")
+    u0 = ix.stats["unresolved"]
+    ids, vals, _ = ix.predict(torch.from_numpy(qq).cuda(), 10, small=False)
+    assert torch.equal(ids, i32) and torch.equal(vals, f32v) and ix.stats["unresolved"] - u0 >= 100, ix.stats
+    hs, hv = ix.predict_host(qq, 10)
+    assert np.array_equal(hs.numpy(), i32.cpu().numpy()) and np.array_equal(hv.numpy(), f32v.cpu().numpy())
+
+
+def test_small_batch_exact_path():
+    """cw_small_predict (thread-per-node FP32 chains, HBM-bound for one query) = the big FP32 kernels bit for bit, for
+    1..32 queries, odd D, through the device call, the host call and cobweb_predict_fast."""
+    for n, d, kind, k in ((900, 100, "unit", 10), (2000, 256, "whitened", 5), (300, 7, "whitened", 1), (600, 1030, "unit", 40)):
+        x = synth.corpus(n, d, kind, seed=31)
+        w = CobwebWrapper(corpus=[None] * n, corpus_embeddings=x)
+        q, _ = synth.queries(x, 40, kind, seed=32)
+        qd = torch.from_numpy(q).cuda()
+        w.build_prediction_index()
+        ix = w._index
+        ids32, v32, _ = ix.predict(qd, k, small=False)
+        for nq in (1, 2, 3, 8, 17, 32):
+            a, b = ix.predict_small(qd[:nq].contiguous(), k)
+            assert torch.equal(a, ids32[:nq]) and torch.equal(b, v32[:nq]), (n, d, nq)
+            hs, hv = ix.predict_host(q[:nq], k)
+            assert np.array_equal(hs.numpy(), ids32[:nq].cpu().numpy()) and np.array_equal(hv.numpy(), v32[:nq].cpu().numpy())
+        assert w.cobweb_predict_fast(q[3], k=k, return_ids=True, is_embedding=True) == list(ids32[3].cpu().numpy())
 
 
 def test_batched_evaluator_on_device():
@@ -572,7 +601,7 @@ def test_batched_evaluator_on_device():
     ids, _ = w.predict_fast_batch(q, 10)
     assert fast["recall@10"] == round(float(np.mean([t in g for t, g in zip(targets, ids.cpu().numpy())])), 4)
     assert fast["recall@2"] <= fast["recall@5"] <= fast["recall@10"] and fast["mrr@10"] <= fast["recall@10"]
-    w.set_dense_mode("tf32x3")
+    w.set_dense_mode("fused")
     assert {k: v for k, v in evaluate_cobweb(w, q, targets, top_k=10, mode="fast").items() if "@" in k} == \
         {k: v for k, v in fast.items() if "@" in k}
     basic = evaluate_cobweb(w, q, targets, top_k=10, mode="basic")
@@ -586,12 +615,10 @@ def test_batched_evaluator_on_device():
 
 @pytest.mark.parametrize("n,d,kind,k,weights", [(6000, 64, "unit", 10, None), (5000, 96, "whitened", 5, [1.0, 0.5, 2.0, 1.5]),
                                                 (700, 128, "unit", 10, None), (3000, 40, "unit", 16, None)])
-def test_fused_tensor_predict_matches_fp32_path(n, d, kind, k, weights):
-    """"tf32x3f": cumulative ancestor sums + leaf scores in the score kernel's epilogue, candidates filtered against
-    a per-query bound from a sample of the leaf tiles (cw_tensor.cu modes 1/2, cw_tc_cumsum_level, cw_tc_select),
-    then the exact re-score: ids and scores bit-identical to the FP32-pipe path.  6000/5000/3000 leaves = sampled
-    tiles exist; 700 = every leaf goes through the filter with an open threshold; duplicated documents = leaves
-    with several sentences."""
+def test_fused_predict_sampled_threshold_and_overflow(n, d, kind, k, weights):
+    """The fused pipeline with a sampled threshold (6000/5000/3000 leaves = sample tiles exist; 700 = every leaf goes
+    through the filter with an open threshold), leaves with several sentences (duplicated documents), level weights,
+    and candidate-buffer overflow: ids and scores bit-identical to the FP32-pipe path."""
     x = synth.corpus(n, d, kind, seed=11)
     x[100:130] = x[7]          # a leaf with 31 sentences
     x[200:203] = x[9]
@@ -604,30 +631,29 @@ def test_fused_tensor_predict_matches_fp32_path(n, d, kind, k, weights):
     w.build_prediction_index()
     ix = w._index
     ids32, v32, _ = ix.predict(qd, k)
-    ix.set_mode("tf32x3f")
-    assert ix.mode == "tf32x3f" and (ix.fx["n_s"] > 0) == (n >= 3000)
-    n0 = ix.n_fallback
+    ix.set_mode("fused")
+    assert ix.mode == "fused" and (ix.hx["n_s"] > 0) == (n >= 3000)
     ids, vals, _ = ix.predict(qd, k)
     assert torch.equal(ids, ids32) and torch.equal(vals, v32)
     hs, hv = ix.predict_host(q, k)
     assert np.array_equal(hs.numpy(), ids32.cpu().numpy()) and np.array_equal(hv.numpy(), v32.cpu().numpy())
-    assert ix.n_fallback - n0 <= 8
-    w.set_dense_mode("tf32x3f")
-    assert w.cobweb_predict_fast(q[5], k=k, return_ids=True, is_embedding=True) == list(ids32[5].cpu().numpy())
-    ix.FUSED_MIN_QUERIES = 1  # the fused pipeline itself on a tiny batch
-    a, b, _ = ix.predict(qd[:3], k)
-    assert torch.equal(a, ids32[:3]) and torch.equal(b, v32[:3])
-    # candidate-buffer overflow: with 8 slots per query nearly every query overflows, is flagged by cw_tc_select and
-    # answered by the unfused path -- same result
-    # (a tree without a sampled tile and with more leaves than slots skips the fused pipeline altogether)
-    ix.FUSED_CAP, ix._ws, e0 = 8, None, ix.n_escalated
+    assert ix.stats["flagged"] <= 16 and ix.stats["audit_mismatch"] == 0, ix.stats
+    if ix.hx["n_s"]:
+        # the sampled threshold really filters: far fewer candidates than leaves
+        assert ix.stats["candidates"] / ix.stats["queries"] < 0.2 * ix.hx["n_leaf"], ix.stats
+    a, b, _ = ix.predict(qd[:40], k, small=False)  # one partial tile
+    assert torch.equal(a, ids32[:40]) and torch.equal(b, v32[:40])
+    # candidate-buffer overflow: with 8 slots per query nearly every query overflows, is flagged by the finish kernel and
+    # answered by the exact path -- same result
+    ix.FUSED_CAP, ix._hws, f0 = 8, None, ix.stats["cand_overflow"]
     a, b, _ = ix.predict(qd, k)
-    assert torch.equal(a, ids32) and torch.equal(b, v32) and (ix.n_escalated - e0 > 100 or ix.fx["n_s"] == 0)
+    assert torch.equal(a, ids32) and torch.equal(b, v32) and ix.stats["cand_overflow"] - f0 > 100
 
 
-def test_tensor_modes_small_and_odd_shapes():
-    """Both tensor modes against the FP32 path on shapes around the tile edges: tiny trees, attribute counts that are
-    not multiples of the 8-attribute slab, k = 1, acuity cutoff, a custom prior variance, one-query batches."""
+def test_fused_predict_small_and_odd_shapes():
+    """The fused mode against the FP32 path on shapes around the tile edges: tiny trees, attribute counts that are not
+    multiples of the 32-feature slab, k = 1, acuity cutoff, a custom prior variance, one-query batches; and a tree whose
+    leaves do NOT have one variance for all attributes (loaded statistics), which takes the general operand layout."""
     cases = [(40, 7, "whitened", 1, {}), (257, 33, "unit", 4, {}), (2500, 200, "unit", 4, dict(acuity_cutoff=True)),
              (900, 9, "whitened", 3, dict(prior_var=0.01)), (3000, 17, "unit", 10, {})]
     for n, d, kind, k, kw in cases:
@@ -640,10 +666,25 @@ def test_tensor_modes_small_and_odd_shapes():
         w.build_prediction_index()
         ix = w._index
         ids32, v32, _ = ix.predict(qd, k)
-        for mode in ("tf32x3", "tf32x3f"):
-            ix.set_mode(mode)
-            ix.FUSED_MIN_QUERIES = 1
-            for batch in (qd, qd[:1]):
-                a, b, _ = ix.predict(batch, k)
-                assert torch.equal(a, ids32[: len(batch)]) and torch.equal(b, v32[: len(batch)]), (n, d, kind, k, mode, len(batch))
-        ix.set_mode("fp32")
+        ix.set_mode("fused")
+        assert ix.hx["leaf_layout"] == 1
+        for batch in (qd, qd[:1]):
+            a, b, _ = ix.predict(batch, k, small=False)
+            assert torch.equal(a, ids32[: len(batch)]) and torch.equal(b, v32[: len(batch)]), (n, d, kind, k, len(batch))
+        assert ix.stats["audit_mismatch"] == 0
+    # anisotropic leaves: perturb the M2 rows of the leaves so that their variances differ per attribute
+    n, d, k = 2000, 48, 10
+    x = synth.corpus(n, d, "whitened", seed=23)
+    w = CobwebWrapper(corpus=[None] * n, corpus_embeddings=x)
+    leaves = torch.as_tensor(np.unique(w._leaf_of_sentence), device="cuda").long()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    w.tree.store.m2[leaves] = 0.05 * torch.rand((len(leaves), d), device="cuda", generator=g)
+    q, _ = synth.queries(x, 300, "whitened", seed=24)
+    qd = torch.from_numpy(q).cuda()
+    w.force_rebuild_index()
+    ix = w._index
+    ids32, v32, _ = ix.predict(qd, k, mode="fp32")
+    ix.set_mode("fused")
+    assert ix.hx["leaf_layout"] == 2
+    a, b, _ = ix.predict(qd, k)
+    assert torch.equal(a, ids32) and torch.equal(b, v32) and ix.stats["audit_mismatch"] == 0

@@ -148,8 +148,13 @@ def test_library_exports_every_declared_symbol():
     assert lib.cw_version() == 100
     assert ctypes.sizeof(_lib.CwStore) == 24 + 12 * 8
     assert lib.cw_topk_chunks(1025) == 3 and lib.cw_xt_floats(129, 20) == 2 * 2 * 16 * 128  # 2 chunks + the threshold slot
-    assert lib.cw_tc_a_bytes(257, 20) == 2 * 3 * 2 * 256 * 64 and lib.cw_tc_b_bytes(300, 9) == 2 * 2 * 2 * 256 * 64
-    assert ctypes.sizeof(_lib.CwTcIndex) == 16 + 4 * 8 + 16 and ctypes.sizeof(_lib.CwDenseWork) == 10 * 8 + 8
+    # fp16 operand sets: layout F1 = 32 attributes per slab, F2 = 16; one-product sets pack two slabs into a stage
+    assert lib.cw_h_stages(768, _lib.H_F1, 1) == 12 and lib.cw_h_stages(768, _lib.H_F2, 3) == 48 and lib.cw_h_stages(33, _lib.H_F1, 1) == 1
+    assert lib.cw_h_a_bytes(257, 20, _lib.H_F2, 3) == 2 * 2 * 32768 and lib.cw_h_b_bytes(300, 9, _lib.H_F1, 1) == 2 * 1 * 32768
+    assert lib.cw_small_scratch_words(1025, 10) == 32 * 3 * 10 * 2
+    assert ctypes.sizeof(_lib.CwDenseWork) == 7 * 8 and ctypes.sizeof(_lib.CwHSet) == 6 * 4 + 2 * 8
+    assert ctypes.sizeof(_lib.CwFusedIndex) == ctypes.sizeof(_lib.CwIndex) + 16 + 2 * 40 + 8 * 8 + 6 * 4
+    assert ctypes.sizeof(_lib.CwFusedWork) == 2 * 8 + 7 * 8 + 8 + 13 * 8 + 8
 
 
 def test_engine_refuses_to_run_without_cuda():
@@ -303,31 +308,37 @@ def test_fused_layout_reproduces_the_path_sums():
     ns = F["n_sample_tiles"]
     n_leaf = len(F["leaf_rows"])
     assert ns == ((n_leaf + 3) // 4) // 64 and ns > 0 and len(F["flat_pos_rec"]) == F["sent_off"][ns * 64]
+    assert np.array_equal(F["leaf_len"], depth[F["leaf_rows"]] + 1) and F["leaf_len"].dtype == np.int32
     assert sorted(F["leaf_rows"].tolist()) == sorted(np.unique(topology.sentence_paths(order, parent_b, depth, leaf_of_sentence, lw, n_slots=n_nodes)["pos_rec"][:, 2]).tolist())
     assert (F["flat_pos_rec"][:, 2] < ns * 64).all() and (np.diff(F["flat_pos_rec"][:, 2]) >= 0).all()
 
 
-def test_candidate_levels_and_adaptation():
-    """Host-side policy of the tensor-core modes (no GPU needed): candidates per query at the two levels, the k range
-    served by the re-score kernel, growth of the first level when a batch escalates too often."""
+def test_fused_mode_host_policy():
+    """Host-side policy of the fused mode (no GPU needed): which requests it serves, how the counters of a call are
+    folded into DenseIndex.stats, and that an audit mismatch widens eps."""
+    import warnings
+    from rag_cobweb_b200 import _lib
     from rag_cobweb_b200.wrapper import DenseIndex
     ix = DenseIndex.__new__(DenseIndex)
-
-    class _Tree:
-        d = 768
-    ix.tree, ix.n_pos, ix.max_len = _Tree(), 1000, 14
-    assert ix.candidates(10) == 24 and ix.candidates(10, 1) == 64 and ix.candidates(10, 2) == 0
-    assert ix.candidates(1) == 24 and ix.candidates(16) == 24 and ix.candidates(20) == 40 and ix.candidates(32) == 64
-    assert ix.candidates(32, 1) == 0          # already at the kernel's maximum: flagged queries go to the FP32 path
-    assert ix.candidates(33) == 0 and ix.candidates(0) == 0
-    ix.max_len = 2000                          # kc * max_len beyond the re-score kernel's 16-bit slots
-    assert ix.candidates(10) == 0
-    ix.max_len = 14
-    ix._adapt(10000, 10)                       # 0.1 % escalated: keep
-    assert ix.candidates(10) == 24
-    ix._adapt(10000, 80)                       # 0.8 %: more first-level candidates
-    assert ix.candidates(10) == 32
-    ix._adapt(10000, 5000)
-    assert ix.candidates(10) == 32             # capped at the fast insertion path's 32
-    ix.n_pos = 0
-    assert ix.candidates(10) == 0
+    ix.mode, ix.nn, ix.hx = "fused", 20000, {"smem_ok": True}
+    assert ix.fused_ready(1) and ix.fused_ready(_lib.FUSED_MAX_K) and not ix.fused_ready(_lib.FUSED_MAX_K + 1) and not ix.fused_ready(0)
+    ix.nn = DenseIndex.TENSOR_MIN_NODES - 1     # small index: the FP32 pipe is the shorter path
+    assert not ix.fused_ready(10)
+    ix.nn, ix.mode = 20000, "fp32"
+    assert not ix.fused_ready(10)
+    ix.stats = {"queries": 0, "flagged": 0, "unresolved": 0, "cand_overflow": 0, "line_fail": 0, "list_overflow": 0,
+                "candidates": 0, "audited": 0, "audit_mismatch": 0}
+    ix.eps_scale = DenseIndex.EPS_SCALE
+    st = np.zeros(_lib.FUSED_STATS, np.int32)
+    st[0], st[2], st[3], st[5], st[8] = 3, 1, 2, 10000, 5
+    st[6:8] = np.array([(1 << 32) + 7], np.uint64).view(np.int32)   # 64-bit candidate counter
+    ix._account(st)
+    assert ix.stats["flagged"] == 3 and ix.stats["cand_overflow"] == 1 and ix.stats["line_fail"] == 2
+    assert ix.stats["queries"] == 10000 and ix.stats["candidates"] == (1 << 32) + 7 and ix.stats["audited"] == 5
+    assert ix.eps_scale == DenseIndex.EPS_SCALE
+    st[:] = 0
+    st[9] = 1
+    with warnings.catch_warnings(record=True) as rec:
+        warnings.simplefilter("always")
+        ix._account(st)
+    assert ix.stats["audit_mismatch"] == 1 and ix.eps_scale == 4 * DenseIndex.EPS_SCALE and len(rec) == 1
