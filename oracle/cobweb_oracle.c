@@ -23,6 +23,9 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #define CO_OP_BEST 0
 #define CO_OP_NEW 1
@@ -866,4 +869,16 @@ void co_topk(const float *scores, long n, int k, int *idx_out, float *val_out) {
         idx_out[j] = (int)i;
         val_out[j] = s;
     }
+}
+
+/* Threads of the dense baseline loops (bench.py sets them explicitly: torchrun exports OMP_NUM_THREADS=1).
+ * Returns the thread count in effect (1 without OpenMP). */
+int co_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
 }

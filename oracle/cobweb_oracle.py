@@ -73,6 +73,14 @@ def lib():
     return _lib
 
 
+def set_threads(n):
+    """OpenMP threads of the dense baseline loops; returns the count in effect (bench.py: all host threads)."""
+    L = lib()
+    L.co_set_threads.restype = C.c_int
+    L.co_set_threads.argtypes = [C.c_int]
+    return int(L.co_set_threads(int(n)))
+
+
 def _f(a):
     return a.ctypes.data_as(C.POINTER(C.c_float))
 

@@ -798,6 +798,45 @@ __global__ void small_scatter_kernel(const int *__restrict__ which, int off, con
         out_val[dst] = sm_val[i];
     }
 }
+
+// Path product + per-chunk top-k for a handful of queries: lane = sentence position (32 positions per step, the
+// levels of a path are independent loads of the [rows, CW_SMALL_Q] score matrix, which sits in L2), the chain
+// acc = fma((float)(level_w[j]/len), s_j, acc) runs root first like paths_topk_kernel's; a warp keeps the running
+// top-k of its chunk in registers (topk_offer).  grid (ceil(n_chunks / 4), queries), 4 warps = 4 chunks per CTA.
+__global__ void __launch_bounds__(128)
+paths_small_kernel(const float *__restrict__ ST, int nq, const int *__restrict__ nq_dev, int n_pos, int max_len,
+                   const int *__restrict__ path_pm, const int4 *__restrict__ pos_rec, const double *__restrict__ level_w, int k,
+                   float *cand_s, int *cand_i, int n_chunks, int chunk_len) {
+    extern __shared__ __align__(16) unsigned char ps_smem[];
+    double *lw = reinterpret_cast<double *>(ps_smem);
+    if (nq_dev) nq = min(nq, *nq_dev);
+    const int q = blockIdx.y;
+    if (q >= nq) return;
+    for (int i = threadIdx.x; i < max_len; i += blockDim.x) lw[i] = level_w[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, chunk = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (chunk >= n_chunks) return;
+    const int p0 = chunk * chunk_len, p1 = min(n_pos, p0 + chunk_len);
+    float ls[PT_SLOTS];
+    int li[PT_SLOTS];
+    topk_init(ls, li);
+    for (int pb = p0; pb < p1; pb += 32) {
+        const int p = pb + lane;
+        float acc = 0.0f;
+        int sid = -1;
+        if (p < p1) {
+            const int4 rc = pos_rec[p];
+            const int len = rc.x;
+            sid = rc.w;
+            const int *path = path_pm + (size_t)p * max_len;
+            const double dl = (double)len;
+            for (int j = 0; j < len; j++)
+                acc = __fmaf_rn((float)(lw[j] / dl), ST[(size_t)path[j] * CW_SMALL_Q + q], acc);
+        }
+        topk_offer(ls, li, k, acc, sid);
+    }
+    topk_store(ls, li, k, cand_s + ((size_t)q * n_chunks + chunk) * k, cand_i + ((size_t)q * n_chunks + chunk) * k);
+}
 }  // namespace cw
 
 extern "C" int64_t cw_small_scratch_words(int64_t n_pos, int k) {
@@ -832,8 +871,26 @@ int cw_small_predict_impl(const cw_index *ix, const float *Q, int64_t nq, const 
         case 16: launch(small_scores_kernel<16>); break;
         default: launch(small_scores_kernel<32>); break;
     }
-    int rc = paths_topk_launch(ix, sm_scores, CW_SMALL_Q, nq, k, nullptr, which ? sm_sid : out_sid, which ? sm_val : out_val,
-                               sm_scratch, cnt, st);
+    // path product + top-k: as many position chunks per query as the scratch holds (more for fewer queries)
+    if (ix->n_pos < 1 || !ix->path_idx || !ix->pos_rec || !ix->level_w || ix->max_len < 1) {
+        cw_set_error("cw_small_predict: the index has no sentence paths");
+        return CW_E_ARG;
+    }
+    const long long slots = (long long)CW_SMALL_Q * (cw_topk_chunks(ix->n_pos) - 1);
+    long long per_q = slots / nq;
+    if (per_q > 1024) per_q = 1024;
+    int chunk_len = (int)((ix->n_pos + per_q - 1) / per_q);
+    if (chunk_len < 256) chunk_len = 256;
+    chunk_len = (chunk_len + 31) & ~31;
+    const int n_chunks = (ix->n_pos + chunk_len - 1) / chunk_len;
+    float *cand_s = reinterpret_cast<float *>(sm_scratch);
+    int *cand_i = sm_scratch + (size_t)nq * n_chunks * k;
+    paths_small_kernel<<<dim3((n_chunks + 3) / 4, (unsigned)nq), 128, (size_t)ix->max_len * sizeof(double), st>>>(
+        sm_scores, (int)nq, cnt, ix->n_pos, ix->max_len, ix->path_idx, reinterpret_cast<const int4 *>(ix->pos_rec), ix->level_w, k,
+        cand_s, cand_i, n_chunks, chunk_len);
+    merge_topk_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, st>>>(cand_s, cand_i, nq, n_chunks, k, which ? sm_sid : out_sid,
+                                                               which ? sm_val : out_val, cnt);
+    int rc = cw_check_cuda(cudaGetLastError(), "cw_small_predict: paths");
     if (rc) return rc;
     if (which && scatter) small_scatter_kernel<<<1, 256, 0, st>>>(which, which_off, sm_n, k, sm_sid, sm_val, out_sid, out_val);
     return cw_check_cuda(cudaGetLastError(), "cw_small_predict");

@@ -30,6 +30,8 @@
 #include <math.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "../../include/cobweb_b200.h"
 
 void cw_set_error(const char *fmt, ...);
@@ -48,7 +50,7 @@ constexpr int NSTAGE = 3;
 constexpr int THREADS = 320;  // producer warp, MMA warp, eight epilogue warps (two per TMEM lane quarter)
 constexpr int EPI_THREADS = THREADS - 64;
 constexpr int REC_FLOATS = 8;
-constexpr int REC_BYTES = 2 * TN * REC_FLOATS * 4;  // two tiles of leaf records
+constexpr int REC_BYTES = 2 * TN * REC_FLOATS * 4 + 64;  // two tiles of leaf records + their run-head masks
 constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */ + REC_BYTES;
 static_assert(IMG == TN * ROWB && SIDE == 2 * IMG, "stage geometry");
 static_assert(EPI_THREADS == TN, "one leaf record per epilogue thread");
@@ -197,6 +199,7 @@ h_score_kernel(const unsigned char *__restrict__ A, const unsigned char *__restr
     const uint32_t tmem_slot = acce + 8;
     uint32_t *tmem_slot_ptr = reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
     float4 *recs_s = reinterpret_cast<float4 *>(smem_raw + (bars + 256 - smem_u32(smem_raw)));  // [2][TN][2]
+    unsigned *heads_s = reinterpret_cast<unsigned *>(recs_s + 2 * TN * 2);                        // [2][8]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -333,11 +336,18 @@ h_score_kernel(const unsigned char *__restrict__ A, const unsigned char *__restr
                 // the tile's leaf records go to shared memory while the MMAs of the tile are still running; two
                 // buffers, so that one named barrier per tile also protects the buffer of the tile before
                 const float4 *recs = recs_s + rbuf * (TN * 2);
+                const unsigned *heads = heads_s + rbuf * 8;
                 {
-                    const int e = threadIdx.x - 64;  // 0..255 over the eight epilogue warps
+                    // rows are in tree order, siblings adjacent: a row whose parent is the previous row's re-uses that
+                    // row's ancestor sum.  heads[c] bit j = row 32 c + j starts a new run of equal parents.
+                    const int e = threadIdx.x - 64;  // 0..255 over the eight epilogue warps: warp e / 32 = 32-row batch
                     const float4 *src = reinterpret_cast<const float4 *>(epi.rc) + (n0 + e) * 2;
+                    const float4 r1 = __ldg(src + 1);
                     recs_s[rbuf * (TN * 2) + e * 2] = __ldg(src);
-                    recs_s[rbuf * (TN * 2) + e * 2 + 1] = __ldg(src + 1);
+                    recs_s[rbuf * (TN * 2) + e * 2 + 1] = r1;
+                    const int par = __float_as_int(r1.y), prev = __shfl_up_sync(0xffffffffu, par, 1);
+                    const unsigned hm = __ballot_sync(0xffffffffu, lane == 0 || par != prev);
+                    if (lane == 0) heads_s[rbuf * 8 + (e >> 5)] = hm;
                     asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
                     rbuf ^= 1;
                 }
@@ -346,21 +356,26 @@ h_score_kernel(const unsigned char *__restrict__ A, const unsigned char *__restr
                 // batch ahead -- the first batch while the MMAs of the tile are still running.  Rows are in tree
                 // order, siblings adjacent: a row whose parent is the previous row's re-uses its value (the parent
                 // index is warp-uniform, so the test is a uniform branch).
+                // issues the loads of the run heads of batch b only (independent, all in flight together); the other
+                // rows take their predecessor's value when the batch is consumed (spread_cp)
                 auto fetch_cp = [&](int b, float (&cp)[32]) {
                     const int qh = b >> 2, c = sub + 2 * (b & 3);
                     const bool qok = (long long)qt * TQ + qh * TM < ldq;
                     const float *Cq = epi.C + qbase + qh * TM;
-                    int prev = -2;
-                    float val = 0.0f;
+                    const unsigned hm = heads[c];
 #pragma unroll
                     for (int j = 0; j < 32; j++) {
-                        const int par = __float_as_int(recs[(c * 32 + j) * 2 + 1].y);  // broadcast read
-                        if (par != prev) {
-                            val = (qok && par >= 0) ? __ldg(Cq + (long long)par * ldq) : 0.0f;
-                            prev = par;
+                        if (hm >> j & 1) {  // warp-uniform
+                            const int par = __float_as_int(recs[(c * 32 + j) * 2 + 1].y);  // broadcast read
+                            cp[j] = (qok && par >= 0) ? __ldg(Cq + (long long)par * ldq) : 0.0f;
                         }
-                        cp[j] = val;
                     }
+                };
+                auto spread_cp = [&](int b, const float (&src)[32], float (&cp)[32]) {
+                    const unsigned hm = heads[sub + 2 * (b & 3)];
+                    cp[0] = src[0];
+#pragma unroll
+                    for (int j = 1; j < 32; j++) cp[j] = (hm >> j & 1) ? src[j] : cp[j - 1];
                 };
                 float4 qv0 = make_float4(0.f, 0.f, 0.f, 0.f), qv1 = qv0;
                 float tau0 = 0.0f, tau1 = 0.0f;
@@ -375,6 +390,8 @@ h_score_kernel(const unsigned char *__restrict__ A, const unsigned char *__restr
 #pragma unroll
                 for (int j = 0; j < 32; j++) smax[j] = -__int_as_float(0x7f800000);
                 float cpn[32];
+#pragma unroll
+                for (int j = 0; j < 32; j++) cpn[j] = 0.0f;
                 fetch_cp(0, cpn);
                 mbar_wait(accf, aphase);
                 tc_fence_after();
@@ -386,8 +403,7 @@ h_score_kernel(const unsigned char *__restrict__ A, const unsigned char *__restr
                     uint32_t v[32];
                     CWH_TMEM_LD32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(qh * TN + c * 32), v);
                     float cp[32];
-#pragma unroll
-                    for (int j = 0; j < 32; j++) cp[j] = cpn[j];
+                    spread_cp(b, cpn, cp);
                     if (b + 1 < 8) fetch_cp(b + 1, cpn);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                     const float4 qv = qh ? qv1 : qv0;
@@ -637,24 +653,24 @@ h_iso_kernel(cw_store s, const int *__restrict__ order, const int *__restrict__ 
 }
 
 // ------------------------------------------------------------------ cumulative ancestor sums, one launch
-// C[n][q] = C[parent(n)][q] + w_n * S[n][q] in place on S.  A CTA owns a strip of 64 queries and walks the internal
+// C[n][q] = C[parent(n)][q] + w_n * S[n][q] in place on S.  A CTA owns a strip of 32 queries and walks the internal
 // rows level by level (rows of one level are independent; the parents of level l are in level l-1, which this CTA
 // finished before the barrier).
-constexpr int CS_COLS = 64;
+constexpr int CS_COLS = 32;
 __global__ void __launch_bounds__(256)
 h_cumsum_kernel(float *S, long long ldq, const int *__restrict__ int_parent, const float *__restrict__ int_w,
                 const int *__restrict__ level_off, int n_levels) {
-    const int q4 = blockIdx.x * CS_COLS + (threadIdx.x & 15) * 4;
+    const int q4 = blockIdx.x * CS_COLS + (threadIdx.x & 7) * 4;
     if (q4 >= ldq) return;
-    const int rl = threadIdx.x >> 4;  // 16 rows per pass
+    const int rl = threadIdx.x >> 3;  // 32 rows per pass
     for (int l = 0; l < n_levels; l++) {
         const int r0 = level_off[l], r1 = level_off[l + 1];
-        for (int rb = r0 + rl; rb < r1; rb += 64) {
+        for (int rb = r0 + rl; rb < r1; rb += 128) {
             float4 sv[4], cv[4];
             float w[4];
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                const int n = rb + 16 * u;
+                const int n = rb + 32 * u;
                 cv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (n < r1) {
                     const int par = int_parent[n];
@@ -665,7 +681,7 @@ h_cumsum_kernel(float *S, long long ldq, const int *__restrict__ int_parent, con
             }
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                const int n = rb + 16 * u;
+                const int n = rb + 32 * u;
                 if (n < r1) {
                     float4 o;
                     o.x = fmaf(w[u], sv[u].x, cv[u].x); o.y = fmaf(w[u], sv[u].y, cv[u].y);
@@ -708,9 +724,7 @@ h_tau_kernel(const int *__restrict__ slots, const float4 *__restrict__ qv, long 
             if (v[j] < last && v[j] > best) best = v[j];
         last = best;
     }
-    const float4 qq = qv[q];
-    const float eps = eps_of(qq.y, inv_prior, hmax, lmax, wfac, eps_scale, max_len);
-    float t = last - 4.0f * (e1max * qq.z + eps);
+    float t = last;
     if (!(last > -1e38f)) t = -__int_as_float(0x7f800000);  // fewer than m sampled rows: no threshold
     tau[q] = t;
 }
@@ -747,8 +761,8 @@ struct FinArgs {
 
 __host__ __device__ inline size_t fin_smem_bytes(int D, int ML, int cap) {
     const size_t E = (size_t)MS * ML;
-    return (size_t)ML * 8 + (size_t)FN_WARPS * 32 * 33 * 8 + (size_t)((D + 3) & ~3) * 4 + (size_t)cap * 8 + (size_t)KC1 * 36 +
-           E * 12 + E * 4 + (size_t)MS * 12 + (size_t)MAXS * 8 + 64;
+    return (size_t)ML * 8 + (size_t)FN_WARPS * 32 * 33 * 8 + (size_t)((D + 3) & ~3) * 4 + (size_t)cap * 14 + (size_t)KC1 * 36 +
+           E * 12 + E * 4 + (size_t)MS * 12 + (size_t)MAXS * 8 + 64 + 16;
 }
 
 __global__ void __launch_bounds__(FN_THREADS)
@@ -760,8 +774,9 @@ h_finish_kernel(const FinArgs a) {
     float *xq = reinterpret_cast<float *>(stage + FN_WARPS * 32 * 33);    // [D]
     float *cv = xq + ((D + 3) & ~3);                                      // [cap] candidate a1
     int *cr = reinterpret_cast<int *>(cv + cap);                          // [cap] candidate leaf row
+    float *ce = reinterpret_cast<float *>(cr + cap);                      // [cap] candidate error bound E
     // selected candidates, best a1 first
-    int *srow = cr + cap;                                                 // [KC1] leaf row
+    int *srow = reinterpret_cast<int *>(ce + cap);                        // [KC1] leaf row
     int *sb = srow + KC1;                                                 // [KC1] index row of the leaf
     float *ss = reinterpret_cast<float *>(sb + KC1);                      // [KC1] exact leaf term
     float *sa3 = ss + KC1;                                                // [KC1]
@@ -781,52 +796,59 @@ h_finish_kernel(const FinArgs a) {
     int *mso = reinterpret_cast<int *>(mex + MS);                         // [MS] offset of its sentences in the list
     int *lsid = mso + MS;                                                 // [MAXS]
     float *lval = reinterpret_cast<float *>(lsid + MAXS);                 // [MAXS]
-    int *misc = reinterpret_cast<int *>(lval + MAXS);                     // ucount, nsurv, nsent, fail code, a1_next bits
+    int *misc = reinterpret_cast<int *>(lval + MAXS);                     // [16] counters and broadcast values
+    unsigned short *byrank = reinterpret_cast<unsigned short *>(misc + 16);  // [cap] candidate with a1 rank r
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float NEG_INF = -__int_as_float(0x7f800000);
     for (int i = tid; i < ML; i += FN_THREADS) lw[i] = a.ix.level_w[i];
 
-    // exact node scores of the rows ulist[0..U) with the FP32 path's arithmetic: rows dealt evenly to the warps,
+    // exact node scores of the rows list[0..U) with the FP32 path's arithmetic: rows dealt evenly to the warps,
     // lane = row; per 32 attributes a warp reads its rows with coalesced 256-byte loads (all in flight at once and one
     // segment ahead of the arithmetic), transposes them through shared memory, every lane runs its row's chain.
-    auto exact_rows = [&](const int *list, int U, float *outs) {
+    // R = rows a warp handles at a time (8, 16 or 32: the loops over rows are unrolled for it).
+    auto exact_rows_r = [&](auto rtag, const int *list, int lo, int n_rows, float *outs) {
+        constexpr int R = decltype(rtag)::value;
         float2 *stw = stage + warp * 32 * 33;
-        for (int base0 = 0; base0 < U; base0 += 32 * FN_WARPS) {
-            const int in_round = min(U - base0, 32 * FN_WARPS);
-            const int per = (in_round + FN_WARPS - 1) / FN_WARPS;
-            const int my_lo = base0 + warp * per;
-            const int my_n = max(0, min(per, base0 + in_round - my_lo));
-            if (my_n == 0) continue;  // warp-uniform
-            const int u = my_lo + lane;
-            const int b = lane < my_n ? list[u] : -1;
+        for (int base0 = lo; base0 < lo + n_rows; base0 += R) {
+            const int u = base0 + lane;
+            const int b = (lane < R && u < lo + n_rows) ? list[u] : -1;
             float acc = 0.0f;
-            float2 o[32];
+            float2 o[R];
             auto fetch = [&](int d0) {
-                const int d = d0 + lane;
 #pragma unroll
-                for (int r = 0; r < 32; r++) {
+                for (int r = 0; r < R; r++) {
                     const int rb = __shfl_sync(0xffffffffu, b, r);
                     o[r] = make_float2(0.0f, 0.0f);
-                    if (rb >= 0 && d < D) o[r] = a.RM[(size_t)rb * D + d];
+                    if (rb >= 0 && d0 + lane < D) o[r] = a.RM[(size_t)rb * D + d0 + lane];
                 }
             };
             fetch(0);
             for (int d0 = 0; d0 < D; d0 += 32) {
 #pragma unroll
-                for (int r = 0; r < 32; r++) stw[r * 33 + lane] = o[r];
+                for (int r = 0; r < R; r++) stw[r * 33 + lane] = o[r];
                 __syncwarp();
                 if (d0 + 32 < D) fetch(d0 + 32);
-                const int nd = min(32, D - d0);
-                for (int j = 0; j < nd; j++) {
-                    const float2 v = stw[lane * 33 + j];
-                    const float t = __fmaf_rn(xq[d0 + j], v.x, v.y);
-                    acc = __fmaf_rn(t, t, acc);
+                if (lane < R) {
+                    const int nd = min(32, D - d0);
+                    for (int j = 0; j < nd; j++) {
+                        const float2 v = stw[lane * 33 + j];
+                        const float t = __fmaf_rn(xq[d0 + j], v.x, v.y);
+                        acc = __fmaf_rn(t, t, acc);
+                    }
                 }
                 __syncwarp();
             }
             if (b >= 0) outs[u] = -0.5f * (a.ix.sumlog[b] + acc);
         }
+    };
+    auto exact_rows = [&](const int *list, int U, float *outs) {
+        const int per = (U + FN_WARPS - 1) / FN_WARPS;
+        const int lo = warp * per, cnt = max(0, min(per, U - lo));
+        if (cnt == 0) return;  // warp-uniform
+        if (per <= 8) exact_rows_r(std::integral_constant<int, 8>{}, list, lo, cnt, outs);
+        else if (per <= 16) exact_rows_r(std::integral_constant<int, 16>{}, list, lo, cnt, outs);
+        else exact_rows_r(std::integral_constant<int, 32>{}, list, lo, cnt, outs);
     };
 
     for (long long q = blockIdx.x; q < a.nq; q += gridDim.x) {
@@ -835,34 +857,60 @@ h_finish_kernel(const FinArgs a) {
         const int n_all = a.cnt[q];
         const int n = min(n_all, cap);
         for (int i = tid; i < n; i += FN_THREADS) { cv[i] = a.cand_val[q * cap + i]; cr[i] = a.cand_row[q * cap + i]; }
-        if (tid < 8) misc[tid] = tid == 4 ? __float_as_int(NEG_INF) : 0;
+        if (tid < 10) misc[tid] = tid == 4 ? 0x7fffffff : (tid == 5 ? float_key(NEG_INF) : 0);
         for (int i = tid; i < KC1; i += FN_THREADS) ssel[i] = -1;
         __syncthreads();
         const float4 qq = a.qv[q];
         const float eps = eps_of(qq.y, a.inv_prior, a.hmax, a.lmax, a.wfac, a.eps_scale, ML);
-        // ---- the best KC1 candidates by a1 (rank = number of candidates that beat it; ties by row)
+        // ---- which candidates need the exact leaf term.  Every candidate has the interval [a1 - E, a1 + E] (E = e1[row] *
+        // ||a_q||, the filter's derived bound) around its leaf score with exact leaf term; L_k = the k-th largest lower end
+        // is a lower bound of the k-th best such score (k different leaves reach it), so a candidate whose upper end stays
+        // 3 eps below L_k cannot reach the line drawn further down and is dropped unrefined.  The rest -- the best KC1
+        // of them by a1 -- is refined.  U = the largest upper end among everything left unrefined (dropped or cut here,
+        // or rejected by the filter: below tau).
+        for (int i = tid; i < n; i += FN_THREADS) ce[i] = a.leaf_rc[cr[i] * 2 + 1].x * qq.z;
+        __syncthreads();
         for (int i = tid; i < n; i += FN_THREADS) {
             const float v = cv[i];
             const int row = cr[i];
             int rank = 0;
             for (int j = 0; j < n; j++) rank += cv[j] > v || (cv[j] == v && cr[j] < row);
-            if (rank < KC1) {
-                srow[rank] = row;
-                sb[rank] = a.leaf_row_b[row];
-                sns[rank] = a.sent_off[row + 1] - a.sent_off[row];
-                const float4 r1 = a.leaf_rc[row * 2 + 1];
-                swl[rank] = r1.z;
-                slen[rank] = __float_as_int(r1.w);
-            } else if (rank == KC1) {
-                misc[4] = __float_as_int(v);  // the best candidate left unrefined
-            }
+            byrank[rank] = (unsigned short)i;
+            // L_k from the k candidates with the best a1 (any k different leaves give a valid lower bound)
+            if (rank < a.k) atomicMin(&misc[4], float_key(v - ce[i] - eps));
         }
         __syncthreads();
-        const int nsel = min(n, KC1);
+        const float Lk = n >= a.k ? key_float(misc[4]) : NEG_INF;
+        if (warp == 0) {
+            // candidates in rank order: the kept ones are compacted into the refine list, the rest raises U
+            int count = 0;
+            float umax = NEG_INF;
+            for (int base = 0; base < n; base += 32) {
+                const int r = base + lane;
+                const int i = r < n ? byrank[r] : -1;
+                const bool keep = i >= 0 && cv[i] + ce[i] + 3.0f * eps >= Lk;
+                const unsigned mask = __ballot_sync(0xffffffffu, keep);
+                const int pos = count + __popc(mask & ((1u << lane) - 1u));
+                count += __popc(mask);
+                if (keep && pos < KC1) {
+                    const int row = cr[i];
+                    srow[pos] = row;
+                    sb[pos] = a.leaf_row_b[row];
+                    sns[pos] = a.sent_off[row + 1] - a.sent_off[row];
+                    const float4 r1 = a.leaf_rc[row * 2 + 1];
+                    swl[pos] = r1.z;
+                    slen[pos] = __float_as_int(r1.w);
+                } else if (i >= 0) {
+                    umax = fmaxf(umax, cv[i] + ce[i]);  // left unrefined
+                }
+            }
+            for (int off = 16; off > 0; off >>= 1) umax = fmaxf(umax, __shfl_xor_sync(0xffffffffu, umax, off));
+            if (lane == 0) { misc[7] = min(count, KC1); misc[5] = float_key(umax); }
+        }
+        __syncthreads();
+        const int nsel = misc[7];
         int fail = n_all > cap ? 1 : 0;  // candidate-buffer overflow
-        // no unrefined leaf scores above U: those cut here have a1 <= a1_next, those the filter dropped a1 + E < tau
-        const float a1_next = __int_as_float(misc[4]);
-        const float U = fmaxf(a.tau[q], a1_next + a.e1max * qq.z);
+        const float U = fmaxf(a.tau[q], key_float(misc[5]));
         // ---- exact leaf terms of the selected candidates, a3 = (C[parent] + w s) / len
         exact_rows(sb, nsel, ss);
         __syncthreads();
@@ -882,12 +930,14 @@ h_finish_kernel(const FinArgs a) {
                 for (int c = 0; c < nsel; c++)
                     if (sa3[c] > v || (sa3[c] == v && c < tid)) before += sns[c];
                 sbefore[tid] = before;
-                if (before < a.k && before + sns[tid] >= a.k) misc[5] = __float_as_int(v), misc[6] = 1;
+                if (before < a.k && before + sns[tid] >= a.k) misc[8] = __float_as_int(v), misc[9] = 1;
             }
             __syncthreads();
-            if (misc[6]) thr = __int_as_float(misc[5]) - 2.0f * eps;
-            // fewer than k sentences among the refined leaves: every one of them is needed, and nothing may be left out
-            if (!(thr > U) && !(U == NEG_INF)) fail = fail ? fail : 2;
+            if (misc[9]) thr = __int_as_float(misc[8]) - 2.0f * eps;
+            // Everything unrefined scores (exactly) at most U + 2 eps, the k-th best exact score is at least A_k - eps: the
+            // answer is complete if U + 3 eps < A_k.  With fewer than k sentences among the refined leaves every one of
+            // them is needed and nothing may be left out (U = -inf).
+            if (!(thr - eps > U) && !(U == NEG_INF)) fail = fail ? fail : 2;
         }
         // ---- survivors: refined leaves at or above the line
         if (tid < nsel && sa3[tid] >= thr) {
@@ -1077,8 +1127,11 @@ int cw_small_predict_impl(const cw_index *ix, const float *Q, int64_t nq, const 
                           float *sm_val, int32_t *sm_n, int32_t *out_sid, float *out_val, cudaStream_t st);
 
 // one chunk of at most w->cap_q queries, all on the device
+// ev (optional): CW_FUSED_STAGES + 1 events recorded at the stage boundaries (cw_fused_profile)
 static int fused_chunk(const cw_fused_index *fi, const cw_fused_work *w, const float *Q, int64_t nq, int k, int32_t *out_sid,
-                       float *out_val, cudaStream_t st) {
+                       float *out_val, cudaStream_t st, cudaEvent_t *ev = nullptr) {
+    auto mark = [&](int i) { if (ev) cudaEventRecord(ev[i], st); };
+    mark(0);
     const int D = fi->ix.D;
     const long long ldq = w->ldq;
     const long long n_pad = (nq + TQ - 1) / TQ * TQ;
@@ -1089,6 +1142,7 @@ static int fused_chunk(const cw_fused_index *fi, const cw_fused_work *w, const f
     hq_build_kernel<<<(unsigned)((n_pad + 7) / 8), 256, 0, st>>>(Q, nq, n_pad, D, fi->leaves.layout,
                                                                 fi->n_int ? reinterpret_cast<unsigned char *>(w->A_int) : nullptr,
                                                                 reinterpret_cast<unsigned char *>(w->A_leaf), qv);
+    mark(1);
     HEpi epi;
     epi.out = w->S;
     epi.ldq = ldq;
@@ -1105,9 +1159,12 @@ static int fused_chunk(const cw_fused_index *fi, const cw_fused_work *w, const f
         epi.rc = fi->internal.rc;
         epi.n_rows = fi->internal.n_rows;
         if ((rc = h_launch<3, EPI_NODE>(&fi->internal, w->A_int, nq, 0, fi->internal.n_ntiles, epi, st))) return rc;
+        mark(2);
         const int strips = (int)((n_pad + CS_COLS - 1) / CS_COLS);
         h_cumsum_kernel<<<strips, 256, 0, st>>>(w->S, ldq, fi->int_parent, fi->int_w, fi->level_off, fi->n_levels);
     }
+    if (!fi->n_int) mark(2);
+    mark(3);
     epi.rc = fi->leaves.rc;
     epi.n_rows = fi->leaves.n_rows;
     const float inv_prior = 1.0f / fi->prior_var;
@@ -1120,7 +1177,9 @@ static int fused_chunk(const cw_fused_index *fi, const cw_fused_work *w, const f
     } else {
         h_fill_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(w->tau, nq, -INFINITY);
     }
+    mark(4);
     if ((rc = h_launch<1, EPI_FILTER>(&fi->leaves, w->A_leaf, nq, 0, fi->leaves.n_ntiles, epi, st))) return rc;
+    mark(5);
     h_stats_kernel<<<32, 256, 0, st>>>(w->cnt, nq, w->stats);
 
     FinArgs a;
@@ -1164,6 +1223,7 @@ static int fused_chunk(const cw_fused_index *fi, const cw_fused_work *w, const f
     const unsigned grid = (unsigned)(nq < 148 * 32 ? nq : 148 * 32);
     h_finish_kernel<<<grid, FN_THREADS, smem, st>>>(a);
     if ((rc = cw_check_cuda(cudaGetLastError(), "cw_fused_predict"))) return rc;
+    mark(6);
     // flagged queries: exact small-batch path, driven by the device-side count
     for (int r = 0; r < CW_FUSED_FB_ROUNDS; r++) {
         if ((rc = cw_small_predict_impl(&fi->ix, Q, CW_SMALL_Q, w->flag + 4, w->flag, r * CW_SMALL_Q, 1, k, w->sm_Q, w->sm_scores,
@@ -1182,6 +1242,7 @@ static int fused_chunk(const cw_fused_index *fi, const cw_fused_work *w, const f
             return rc;
         h_audit_cmp_kernel<<<1, CW_SMALL_Q, 0, st>>>(which, (int)n_a, k, w->sm_sid, w->sm_val, out_sid, out_val, w->stats);
     }
+    mark(7);
     return cw_check_cuda(cudaGetLastError(), "cw_fused_predict: tail");
 }
 
@@ -1262,4 +1323,23 @@ extern "C" int cw_fused_predict_host(const cw_fused_index *fi, const cw_fused_wo
     if (stats_host)
         for (int i = 0; i < CW_FUSED_STATS; i++) stats_host[i] = stats[i];
     return 0;
+}
+
+// One chunk with CUDA events at the stage boundaries; synchronises.  stage_ms[CW_FUSED_STAGES]: query operands,
+// internal-row scores (fp16 x3), cumulative sums, sampled tiles + threshold, leaf filter (fp16 x1), finish (select /
+// refine / exact re-score), tail (device-side fallback rounds, audit).
+extern "C" int cw_fused_profile(const cw_fused_index *fi, const cw_fused_work *w, const float *Q, int64_t nq, int k,
+                                int32_t *out_sid, float *out_val, float *stage_ms_host, void *stream) {
+    if (!fused_args_ok(fi, w, k) || !Q || !out_sid || !out_val || !stage_ms_host || nq < 1 || nq > w->cap_q) {
+        cw_set_error("cw_fused_profile: bad argument (one chunk: nq <= cap_q)");
+        return CW_E_ARG;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaEvent_t ev[CW_FUSED_STAGES + 1];
+    for (auto &e : ev) cudaEventCreate(&e);
+    int rc = fused_chunk(fi, w, Q, nq, k, out_sid, out_val, st, ev);
+    if (!rc) rc = cw_check_cuda(cudaStreamSynchronize(st), "cw_fused_profile: sync");
+    for (int i = 0; i < CW_FUSED_STAGES && !rc; i++) cudaEventElapsedTime(stage_ms_host + i, ev[i], ev[i + 1]);
+    for (auto &e : ev) cudaEventDestroy(e);
+    return rc;
 }

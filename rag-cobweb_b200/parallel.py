@@ -39,26 +39,41 @@ def broadcast_store(tree, src=0):
     s._struct = None
 
 
-def gather_results(ids, vals, counts=None):
-    """All-gather per-rank [q_r, k] results into the full batch order.  Shards may differ in
-    size by one row (shard_bounds): rows are padded to the largest shard for the collective."""
-    world = dist.get_world_size()
-    if world == 1:
+class ResultGather:
+    """All-gather of the per-rank [q_r, k] results into the full batch order: ONE collective on one packed buffer.
+
+    The shard sizes follow from shard_bounds(total, world, r) on every rank, so nothing is exchanged to learn them and
+    nothing is read back to the host; ids (int32) and scores (float32 bit patterns) travel in one [rows, 2k] int32
+    buffer.  Buffers are allocated once and re-used by every call."""
+
+    def __init__(self, total, k, world=None, device="cuda"):
+        self.world = world if world is not None else dist.get_world_size()
+        self.k, self.total = k, total
+        self.sizes = [shard_bounds(total, self.world, r)[1] - shard_bounds(total, self.world, r)[0] for r in range(self.world)]
+        self.m = max(self.sizes) if self.sizes else 0
+        self.send = torch.empty((self.m, 2 * k), dtype=torch.int32, device=device)
+        self.recv = torch.empty((self.world * self.m, 2 * k), dtype=torch.int32, device=device)
+        self.keep = None
+        if min(self.sizes) != self.m:  # uneven shards: rows of the padded layout that are real
+            self.keep = torch.cat([torch.arange(r * self.m, r * self.m + self.sizes[r], device=device)
+                                   for r in range(self.world)])
+
+    def __call__(self, ids, vals):
+        if self.world == 1:
+            return ids, vals
+        n, k = ids.shape[0], self.k
+        self.send[:n, :k] = ids
+        self.send[:n, k:] = vals.view(torch.int32)
+        dist.all_gather_into_tensor(self.recv, self.send)
+        out = self.recv if self.keep is None else self.recv[self.keep]
+        return out[:, :k], out[:, k:].view(torch.float32)
+
+
+def gather_results(ids, vals, total):
+    """One-off form of ResultGather: `total` = rows of the whole batch (this rank holds its shard_bounds share)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return ids, vals
-    q_r = torch.tensor([ids.shape[0]], dtype=torch.int64, device=ids.device)
-    sizes = [torch.zeros_like(q_r) for _ in range(world)]
-    dist.all_gather(sizes, q_r)
-    sizes = [int(s.item()) for s in sizes]
-    m, k = max(sizes), ids.shape[1]
-    pid = torch.full((m, k), -1, dtype=ids.dtype, device=ids.device)
-    pva = torch.full((m, k), float("-inf"), dtype=vals.dtype, device=vals.device)
-    pid[: ids.shape[0]], pva[: vals.shape[0]] = ids, vals
-    gi = torch.empty((world * m, k), dtype=ids.dtype, device=ids.device)
-    gv = torch.empty((world * m, k), dtype=vals.dtype, device=vals.device)
-    dist.all_gather_into_tensor(gi, pid)
-    dist.all_gather_into_tensor(gv, pva)
-    keep = torch.cat([torch.arange(r * m, r * m + sizes[r], device=ids.device) for r in range(world)])
-    return gi[keep], gv[keep]
+    return ResultGather(total, ids.shape[1], device=ids.device)(ids, vals)
 
 
 def merge_topk(ids, vals, k):
@@ -74,17 +89,15 @@ def merge_topk(ids, vals, k):
 
 
 def gather_candidates(ids, vals):
-    """All-gather [q, k] candidate lists of every rank along the candidate axis -> [q, world*k]."""
+    """All-gather [q, k] candidate lists of every rank along the candidate axis -> [q, world*k]; ids and score bits
+    packed into one buffer, one collective."""
     world = dist.get_world_size()
     if world == 1:
         return ids, vals
-    gi = [torch.empty_like(ids) for _ in range(world)]
-    gv = [torch.empty_like(vals) for _ in range(world)]
-    dist.all_gather(gi, ids)
-    dist.all_gather(gv, vals)
-    return torch.cat(gi, 1), torch.cat(gv, 1)
-
-
-def partition_sentences(leaf_row_sorted_pos, world, rank):
-    """Sentence positions (already in tree order) owned by `rank` in the store-sharded mode."""
-    return shard_bounds(len(leaf_row_sorted_pos), world, rank)
+    q, k = ids.shape
+    send = torch.cat([ids, vals.view(torch.int32)], 1).contiguous()
+    recv = torch.empty((world, q, 2 * k), dtype=torch.int32, device=ids.device)
+    dist.all_gather_into_tensor(recv.view(world * q, 2 * k), send)
+    gi = recv[:, :, :k].permute(1, 0, 2).reshape(q, world * k)
+    gv = recv[:, :, k:].permute(1, 0, 2).reshape(q, world * k).contiguous().view(torch.float32)
+    return gi, gv

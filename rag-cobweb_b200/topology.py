@@ -176,6 +176,8 @@ def fused_layout(order, parent_b, depth, leaf_of_sentence, level_weights=None, n
     # read together), the partial last tile is theirs
     leaves = np.nonzero(is_leaf)[0]
     n_leaf = len(leaves)
+    if n_leaf < sample_every * tile and n_leaf >= 2 * tile:
+        sample_every = n_leaf // tile  # small index: one sampled tile with a coarser stride
     samp = np.arange(0, n_leaf, sample_every, dtype=np.int64)
     n_s_tiles = len(samp) // tile if n_leaf >= sample_every * tile else 0
     samp = samp[: n_s_tiles * tile]

@@ -379,6 +379,33 @@ class DenseIndex:
                                              ws["scratch"].data_ptr(), _lib.stream_ptr()), "cw_dense_paths_topk")
         return sids, vals, leaf
 
+    def predict_one(self, q, k):
+        """One query (contiguous float32 numpy row) -> list of k sentence ids: the shortest way through the exact
+        small-batch path (one C call: H2D, two kernels + merge, D2H, sync; no torch objects created)."""
+        sm = self.small_workspace(k)
+        sid, val = sm["sid_host"], sm["val_host"]
+        _lib.check(_lib.load().cw_small_predict_host(C.byref(self.ix), q.ctypes.data, 1, k, sm["Q"].data_ptr(),
+                                                     sm["scores"].data_ptr(), sm["scratch"].data_ptr(), sm["sid"].data_ptr(),
+                                                     sm["val"].data_ptr(), sm["n"].data_ptr(), sid.data_ptr(), val.data_ptr(),
+                                                     _lib.stream_ptr()), "cw_small_predict_host")
+        return sid.view(-1)[:k].tolist()
+
+    STAGES = ("query_operands", "internal_scores_f16x3", "cumulative_sums", "sample_threshold", "leaf_filter_f16", "finish",
+              "fallback_audit_tail")
+
+    def profile_stages(self, Q, k):
+        """Per-stage device times (ms, CUDA events inside cw_fused_profile) of ONE fused chunk: dict stage -> ms."""
+        hw = self.fused_workspace(Q.shape[0], k)
+        if Q.shape[0] > hw["cap_q"]:
+            raise ValueError("profile_stages takes one chunk")
+        fi, w = self._fused_struct(hw)
+        sids = torch.empty((Q.shape[0], k), dtype=torch.int32, device=Q.device)
+        vals = torch.empty((Q.shape[0], k), dtype=torch.float32, device=Q.device)
+        ms = (C.c_float * _lib.FUSED_STAGES)()
+        _lib.check(_lib.load().cw_fused_profile(C.byref(fi), C.byref(w), Q.data_ptr(), Q.shape[0], k, sids.data_ptr(),
+                                                vals.data_ptr(), ms, _lib.stream_ptr()), "cw_fused_profile")
+        return dict(zip(self.STAGES, [float(v) for v in ms]))
+
     def predict_host(self, Q_host, k, out_sid=None, out_val=None):
         """Host batch (numpy / pinned tensor) -> host ids/scores through ONE C-ABI call per batch:
         cw_fused_predict_host ("fused" mode), cw_small_predict_host (up to SMALL_Q queries) or cw_predict_dense_host
@@ -664,9 +691,19 @@ class CobwebWrapper:
         self.build_prediction_index()
         if len(self.sentences) == 0:
             return []
-        ids, _ = self.predict_fast_batch(self._embed(input, is_embedding), k)
+        kk = min(int(k), self._index.n_pos)
+        if 1 <= kk <= _lib.MAX_K:
+            emb = input if is_embedding else self.encode_func([input])[0]
+            emb = emb.detach().cpu().numpy() if torch.is_tensor(emb) else emb
+            q = np.ascontiguousarray(emb, dtype=np.float32).reshape(-1)
+            if q.shape[0] != self.tree.d:
+                raise ValueError(f"instance dim {q.shape[0]} != tree dim {self.tree.d}")
+            sids = self._index.predict_one(q, kk)
+        else:
+            ids, _ = self.predict_fast_batch(self._embed(input, is_embedding), k)
+            sids = ids[0].cpu().tolist()
         out = []
-        for sid in ids[0].cpu().tolist():
+        for sid in sids:
             if 0 <= sid < len(self.sentences):
                 out.append(sid if return_ids else self.sentences[sid])
         return out

@@ -208,9 +208,14 @@ def _worker(rank, world, port, q, ret):
         # query-sharded mode: each rank answers its shard, one all-gather returns the batch
         lo, hi = parallel.shard_bounds(q, world, rank)
         ids, vals = local_predict(qs[lo:hi])
-        gi, gv = parallel.gather_results(ids, vals)
+        gi, gv = parallel.gather_results(ids, vals, q)
         full_i, full_v = local_predict(qs)
         ok1 = torch.equal(gi, full_i) and torch.equal(gv, full_v)
+        # the re-usable form: sizes from shard_bounds, one packed collective, same buffers on every call
+        g = parallel.ResultGather(q, k, device="cpu")
+        for _ in range(2):
+            gi2, gv2 = g(ids, vals)
+            ok1 = ok1 and torch.equal(gi2, full_i) and torch.equal(gv2, full_v)
         # store-sharded mode: each rank scores only its sentences, candidates merged after all-gather
         _, ls = t.dense_scores(qs)
         slo, shi = parallel.shard_bounds(ls.shape[1], world, rank)

@@ -108,3 +108,12 @@ t_s1 = timed(lambda: ix.predict_small(qd[:1], k), reps=20)
 t_s32 = timed(lambda: ix.predict_small(qd[:32], k), reps=10)
 print(f"timing: fused {t_f:.3f} ms ({nq / t_f * 1e3:.0f} q/s), fp32 {t_32:.3f} ms, small(1) {t_s1:.3f} ms, small(32) {t_s32:.3f} ms")
 print("stats", ix.stats)
+for rep in range(2):
+    print("stages (ms):", {k_: round(v, 3) for k_, v in ix.profile_stages(qd[: ix.fused_workspace(nq, k)["cap_q"]], k).items()})
+t_h = timed(lambda: ix.predict_host(q, k))
+print(f"host entry: {t_h:.3f} ms ({nq / t_h * 1e3:.0f} q/s)")
+import time
+t0 = time.time()
+for i in range(50):
+    w.cobweb_predict_fast(q[i % nq], k=k, return_ids=True, is_embedding=True)
+print(f"cobweb_predict_fast single query: {(time.time() - t0) / 50 * 1e3:.3f} ms")
