@@ -47,13 +47,15 @@ constexpr int IMG = CW_H_IMG_BYTES;
 constexpr int SIDE = CW_H_STAGE_BYTES;  // A resp. B part of a stage: two images
 constexpr int STAGE_BYTES = 2 * SIDE;   // 64 KB
 constexpr int NSTAGE = 3;
-constexpr int THREADS = 320;  // producer warp, MMA warp, eight epilogue warps (two per TMEM lane quarter)
+constexpr int EPI_WARPS = 16;   // four per TMEM lane quarter
+constexpr int THREADS = 64 + 32 * EPI_WARPS;  // producer warp, MMA warp, epilogue warps
 constexpr int EPI_THREADS = THREADS - 64;
+constexpr int BW = 16;          // accumulator columns (index rows) an epilogue thread handles at a time
 constexpr int REC_FLOATS = 8;
-constexpr int REC_BYTES = 2 * TN * REC_FLOATS * 4 + 64;  // two tiles of leaf records + their run-head masks
+constexpr int REC_BYTES = 2 * TN * REC_FLOATS * 4 + 2 * TN * 8 + 128;  // two tiles of leaf records, parent-row byte offsets, run masks
 constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */ + REC_BYTES;
 static_assert(IMG == TN * ROWB && SIDE == 2 * IMG, "stage geometry");
-static_assert(EPI_THREADS == TN, "one leaf record per epilogue thread");
+static_assert(EPI_THREADS >= TN && EPI_WARPS % 4 == 0 && BW * 2 == 32, "epilogue geometry");
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -135,6 +137,15 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
         : "r"(taddr)                                                                                               \
         : "memory")
 
+#define CWH_TMEM_LD16(taddr, v)                                                                                    \
+    asm volatile(                                                                                                  \
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "                                                                  \
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"                           \
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),          \
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])     \
+        : "r"(taddr)                                                                                               \
+        : "memory")
+
 // byte offset of 16-byte chunk c (0..3) of row r inside a 64-byte-swizzled operand image: address bits [7,9)
 // (row / 2 within the 8-row group) are XORed into the chunk bits [4,6)
 __device__ __forceinline__ int swz_off(int r, int c) { return r * ROWB + ((c ^ ((r >> 1) & 3)) << 4); }
@@ -199,7 +210,8 @@ h_score_kernel(const unsigned char *__restrict__ A, const unsigned char *__restr
     const uint32_t tmem_slot = acce + 8;
     uint32_t *tmem_slot_ptr = reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
     float4 *recs_s = reinterpret_cast<float4 *>(smem_raw + (bars + 256 - smem_u32(smem_raw)));  // [2][TN][2]
-    unsigned *heads_s = reinterpret_cast<unsigned *>(recs_s + 2 * TN * 2);                        // [2][8]
+    long long *coff_s = reinterpret_cast<long long *>(recs_s + 2 * TN * 2);                       // [2][TN]
+    unsigned *heads_s = reinterpret_cast<unsigned *>(coff_s + 2 * TN);                            // [2][8] run heads, [2][8] heads to load
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -297,9 +309,11 @@ h_score_kernel(const unsigned char *__restrict__ A, const unsigned char *__restr
         }
         __syncwarp();
     } else {
-        // ===== epilogue: warp w reads TMEM lanes 32*(w%4) .. +31 (lane = query of the 128-query half); the two
-        // warps of a quarter take alternate 32-column batches
-        const int quarter = warp & 3, sub = (warp - 2) >> 2;
+        // ===== epilogue: sixteen warps; warp w reads TMEM lanes 32*(w%4) .. +31 (lane = query of the 128-query half),
+        // the four warps of a lane quarter take every fourth 16-column block.  The work per (query, row) is a dozen
+        // dependent instructions on two shared-memory reads: latency-bound, so the more warps the better; 16 columns at
+        // a time keep a thread under the 112 registers that 576 threads per SM allow.
+        const int quarter = warp & 3, sub = (warp - 2) >> 2;  // sub 0..3
         uint32_t aphase = 0;
         int rbuf = 0;
         const long long ldq = epi.ldq;
@@ -320,13 +334,13 @@ h_score_kernel(const unsigned char *__restrict__ A, const unsigned char *__restr
                     const long long q = qbase + qh * TM;
                     const float sa = epi.qv[q].w;
 #pragma unroll 1
-                    for (int c = sub; c < TN / 32; c += 2) {
-                        uint32_t v[32];
-                        CWH_TMEM_LD32(taddr + (uint32_t)(c * 32), v);
+                    for (int cb = sub; cb < TN / BW; cb += EPI_WARPS / 4) {
+                        uint32_t v[BW];
+                        CWH_TMEM_LD16(taddr + (uint32_t)(cb * BW), v);
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                        for (int j = 0; j < 32; j++) {
-                            const long long n = n0 + c * 32 + j;
+                        for (int j = 0; j < BW; j++) {
+                            const long long n = n0 + cb * BW + j;
                             const float2 r = __ldg(rc2 + n);
                             epi.out[n * ldq + q] = fmaf(__uint_as_float(v[j]) * sa, r.y, r.x);
                         }
@@ -336,46 +350,52 @@ h_score_kernel(const unsigned char *__restrict__ A, const unsigned char *__restr
                 // the tile's leaf records go to shared memory while the MMAs of the tile are still running; two
                 // buffers, so that one named barrier per tile also protects the buffer of the tile before
                 const float4 *recs = recs_s + rbuf * (TN * 2);
-                const unsigned *heads = heads_s + rbuf * 8;
+                const long long *coff = coff_s + rbuf * TN;
+                const unsigned *heads = heads_s + rbuf * 16;
                 {
                     // rows are in tree order, siblings adjacent: a row whose parent is the previous row's re-uses that
-                    // row's ancestor sum.  heads[c] bit j = row 32 c + j starts a new run of equal parents.
-                    const int e = threadIdx.x - 64;  // 0..255 over the eight epilogue warps: warp e / 32 = 32-row batch
-                    const float4 *src = reinterpret_cast<const float4 *>(epi.rc) + (n0 + e) * 2;
-                    const float4 r1 = __ldg(src + 1);
-                    recs_s[rbuf * (TN * 2) + e * 2] = __ldg(src);
-                    recs_s[rbuf * (TN * 2) + e * 2 + 1] = r1;
-                    const int par = __float_as_int(r1.y), prev = __shfl_up_sync(0xffffffffu, par, 1);
-                    const unsigned hm = __ballot_sync(0xffffffffu, lane == 0 || par != prev);
-                    if (lane == 0) heads_s[rbuf * 8 + (e >> 5)] = hm;
+                    // row's ancestor sum.  heads[c] bit j = row 32 c + j starts a new run of equal parents; heads[8 + c] =
+                    // those of them that have a parent row to load; coff = byte offset of that row of C.
+                    const int e = threadIdx.x - 64;  // the first 256 epilogue threads: one row each
+                    if (e < TN) {
+                        const float4 *src = reinterpret_cast<const float4 *>(epi.rc) + (n0 + e) * 2;
+                        const float4 r1 = __ldg(src + 1);
+                        recs_s[rbuf * (TN * 2) + e * 2] = __ldg(src);
+                        recs_s[rbuf * (TN * 2) + e * 2 + 1] = r1;
+                        const int par = __float_as_int(r1.y), prev = __shfl_up_sync(0xffffffffu, par, 1);
+                        coff_s[rbuf * TN + e] = (long long)(par < 0 ? 0 : par) * ldq * 4;
+                        const bool head = (lane & (BW - 1)) == 0 || par != prev;
+                        const unsigned hm = __ballot_sync(0xffffffffu, head), lm = __ballot_sync(0xffffffffu, head && par >= 0);
+                        if (lane == 0) { heads_s[rbuf * 16 + (e >> 5)] = hm; heads_s[rbuf * 16 + 8 + (e >> 5)] = lm; }
+                    }
                     asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
                     rbuf ^= 1;
                 }
-                // This warp's eight batches of 32 rows: b -> (query half b / 4, column block sub + 2 (b % 4)).  The
-                // ancestor sums C[parent][q] of a batch do not depend on the accumulator, so they are fetched one
-                // batch ahead -- the first batch while the MMAs of the tile are still running.  Rows are in tree
-                // order, siblings adjacent: a row whose parent is the previous row's re-uses its value (the parent
-                // index is warp-uniform, so the test is a uniform branch).
-                // issues the loads of the run heads of batch b only (independent, all in flight together); the other
-                // rows take their predecessor's value when the batch is consumed (spread_cp)
-                auto fetch_cp = [&](int b, float (&cp)[32]) {
-                    const int qh = b >> 2, c = sub + 2 * (b & 3);
+                // This warp's eight batches of 16 rows: b -> (query half b / 4, column block sub + 4 (b % 4)).  The
+                // ancestor sums C[parent][q] of a batch do not depend on the accumulator, so they are fetched one batch
+                // ahead -- the first batch while the MMAs of the tile are still running -- and only for the run heads
+                // (predicated loads, all in flight together); the other rows carry their predecessor's value along.
+                auto heads_of = [&](int b) { const int cb = sub + 4 * (b & 3); return (heads[cb >> 1] >> ((cb & 1) * BW)) & 0xffffu; };
+                auto fetch_cp = [&](int b, float (&cp)[BW]) {
+                    const int qh = b >> 2, cb = sub + 4 * (b & 3);
                     const bool qok = (long long)qt * TQ + qh * TM < ldq;
-                    const float *Cq = epi.C + qbase + qh * TM;
-                    const unsigned hm = heads[c];
+                    const char *Cq = reinterpret_cast<const char *>(epi.C + qbase + qh * TM);
+                    const unsigned lm = qok ? (heads[8 + (cb >> 1)] >> ((cb & 1) * BW)) & 0xffffu : 0u;
 #pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        if (hm >> j & 1) {  // warp-uniform
-                            const int par = __float_as_int(recs[(c * 32 + j) * 2 + 1].y);  // broadcast read
-                            cp[j] = (qok && par >= 0) ? __ldg(Cq + (long long)par * ldq) : 0.0f;
-                        }
+                    for (int j = 0; j < BW; j++) {
+                        const char *ptr = Cq + coff[cb * BW + j];  // broadcast read
+                        const unsigned go = lm & (1u << j);
+                        float val = 0.0f;
+                        asm volatile(
+                            "{\n"
+                            ".reg .pred p;\n"
+                            "setp.ne.u32 p, %2, 0;\n"
+                            "@p ld.global.nc.f32 %0, [%1];\n"
+                            "}\n"
+                            : "+f"(val)
+                            : "l"(ptr), "r"(go));
+                        cp[j] = val;
                     }
-                };
-                auto spread_cp = [&](int b, const float (&src)[32], float (&cp)[32]) {
-                    const unsigned hm = heads[sub + 2 * (b & 3)];
-                    cp[0] = src[0];
-#pragma unroll
-                    for (int j = 1; j < 32; j++) cp[j] = (hm >> j & 1) ? src[j] : cp[j - 1];
                 };
                 float4 qv0 = make_float4(0.f, 0.f, 0.f, 0.f), qv1 = qv0;
                 float tau0 = 0.0f, tau1 = 0.0f;
@@ -386,55 +406,57 @@ h_score_kernel(const unsigned char *__restrict__ A, const unsigned char *__restr
                     if (live0) tau0 = epi.tau[qbase];
                     if (live1) tau1 = epi.tau[qbase + TM];
                 }
-                float smax[32];
+                float smax[BW];  // TAU: this warp only ever sees the rows r with (r / 16) % 4 == sub: slots (sub & 1) * 16 + j
 #pragma unroll
-                for (int j = 0; j < 32; j++) smax[j] = -__int_as_float(0x7f800000);
-                float cpn[32];
-#pragma unroll
-                for (int j = 0; j < 32; j++) cpn[j] = 0.0f;
+                for (int j = 0; j < BW; j++) smax[j] = -__int_as_float(0x7f800000);
+                float cpn[BW];
                 fetch_cp(0, cpn);
                 mbar_wait(accf, aphase);
                 tc_fence_after();
 #pragma unroll 1
                 for (int b = 0; b < 8; b++) {
-                    const int qh = b >> 2, c = sub + 2 * (b & 3);
+                    const int qh = b >> 2, cb = sub + 4 * (b & 3);
                     if ((long long)qt * TQ + qh * TM >= ldq) break;  // a half-tile of pure padding past the score matrix
                     const long long q = qbase + qh * TM;
-                    uint32_t v[32];
-                    CWH_TMEM_LD32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(qh * TN + c * 32), v);
-                    float cp[32];
-                    spread_cp(b, cpn, cp);
+                    uint32_t v[BW];
+                    CWH_TMEM_LD16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(qh * TN + cb * BW), v);
+                    float cur[BW];
+#pragma unroll
+                    for (int j = 0; j < BW; j++) cur[j] = cpn[j];
+                    const unsigned hm = heads_of(b);
                     if (b + 1 < 8) fetch_cp(b + 1, cpn);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                     const float4 qv = qh ? qv1 : qv0;
                     const float tau = qh ? tau1 : tau0;
                     const bool live = qh ? live1 : live0;
-                    float sc[32];
+                    float sc[BW];
                     unsigned hit = 0;
+                    float c = 0.0f;
 #pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        const float4 r0 = recs[(c * 32 + j) * 2];      // {alpha, beta, gamma, delta}, broadcast read
-                        const float e1 = recs[(c * 32 + j) * 2 + 1].x;
+                    for (int j = 0; j < BW; j++) {
+                        const float4 r0 = recs[(cb * BW + j) * 2];      // {alpha, beta, gamma, delta}, broadcast read
+                        const float e1 = recs[(cb * BW + j) * 2 + 1].x;
+                        c = (hm & (1u << j)) ? cur[j] : c;             // ancestor sum of this row's run
                         const float t0 = fmaf(r0.z, qv.y, r0.y);       // beta + gamma |x|^2
-                        const float t1 = fmaf(r0.w, cp[j], t0);        // + C[parent] / len
+                        const float t1 = fmaf(r0.w, c, t0);            // + C[parent] / len
                         sc[j] = fmaf(r0.x, __uint_as_float(v[j]) * qv.x, t1);
                         if (MODE == EPI_TAU) smax[j] = fmaxf(smax[j], sc[j]);
                         else if (fmaf(e1, qv.z, sc[j]) >= tau) hit |= 1u << j;
                     }
                     if (MODE == EPI_FILTER) {
                         // rows past the set are tile padding (only in the last tile)
-                        const long long left = (long long)epi.n_rows - (n0 + c * 32);
-                        if (left < 32) hit &= left <= 0 ? 0u : (1u << left) - 1u;
+                        const long long left = (long long)epi.n_rows - (n0 + cb * BW);
+                        if (left < BW) hit &= left <= 0 ? 0u : (1u << left) - 1u;
                         if (live && hit) {
                             // one counter update per thread and batch: a returning atomic per hit would put an L2
                             // round trip between the rows
                             int at = atomicAdd(epi.cnt + q, __popc(hit));
 #pragma unroll
-                            for (int j = 0; j < 32; j++) {
+                            for (int j = 0; j < BW; j++) {
                                 if (hit >> j & 1) {
                                     if (at < epi.cap) {
                                         epi.cand_val[q * epi.cap + at] = sc[j];
-                                        epi.cand_row[q * epi.cap + at] = (int)(n0 + c * 32 + j);
+                                        epi.cand_row[q * epi.cap + at] = (int)(n0 + cb * BW + j);
                                     }
                                     at++;
                                 }
@@ -444,20 +466,20 @@ h_score_kernel(const unsigned char *__restrict__ A, const unsigned char *__restr
                     if (MODE == EPI_TAU && (b & 3) == 3) {
                         // this query half is done: publish the slot maxima that beat what the slots already hold
                         if (live) {
-                            int *sl = epi.slots + q * 32;
+                            int *sl = epi.slots + q * 32 + (sub & 1) * BW;
 #pragma unroll
-                            for (int j4 = 0; j4 < 8; j4++) {
-                                const int4 cur = __ldcg(reinterpret_cast<const int4 *>(sl) + j4);
+                            for (int j4 = 0; j4 < BW / 4; j4++) {
+                                const int4 cur4 = __ldcg(reinterpret_cast<const int4 *>(sl) + j4);
                                 const int k0 = float_key(smax[4 * j4]), k1 = float_key(smax[4 * j4 + 1]);
                                 const int k2 = float_key(smax[4 * j4 + 2]), k3 = float_key(smax[4 * j4 + 3]);
-                                if (k0 > cur.x) atomicMax(sl + 4 * j4, k0);
-                                if (k1 > cur.y) atomicMax(sl + 4 * j4 + 1, k1);
-                                if (k2 > cur.z) atomicMax(sl + 4 * j4 + 2, k2);
-                                if (k3 > cur.w) atomicMax(sl + 4 * j4 + 3, k3);
+                                if (k0 > cur4.x) atomicMax(sl + 4 * j4, k0);
+                                if (k1 > cur4.y) atomicMax(sl + 4 * j4 + 1, k1);
+                                if (k2 > cur4.z) atomicMax(sl + 4 * j4 + 2, k2);
+                                if (k3 > cur4.w) atomicMax(sl + 4 * j4 + 3, k3);
                             }
                         }
 #pragma unroll
-                        for (int j = 0; j < 32; j++) smax[j] = -__int_as_float(0x7f800000);
+                        for (int j = 0; j < BW; j++) smax[j] = -__int_as_float(0x7f800000);
                     }
                 }
             }
@@ -735,6 +757,7 @@ __global__ void h_fill_kernel(float *p, long long n, float v) {
 
 // ------------------------------------------------------------------ finish: select, refine, line test, exact re-score
 constexpr int FN_THREADS = 128, FN_WARPS = FN_THREADS / 32;
+constexpr int FN_R = 16;  // rows a warp of the finish kernel scores exactly at a time (sizes its transposition buffer)
 constexpr int KC1 = CW_FUSED_KC1, MS = CW_FUSED_MSURV, MAXS = CW_FUSED_MAX_SENT;
 
 struct FinArgs {
@@ -761,7 +784,7 @@ struct FinArgs {
 
 __host__ __device__ inline size_t fin_smem_bytes(int D, int ML, int cap) {
     const size_t E = (size_t)MS * ML;
-    return (size_t)ML * 8 + (size_t)FN_WARPS * 32 * 33 * 8 + (size_t)((D + 3) & ~3) * 4 + (size_t)cap * 14 + (size_t)KC1 * 36 +
+    return (size_t)ML * 8 + (size_t)FN_WARPS * FN_R * 33 * 8 + (size_t)((D + 3) & ~3) * 4 + (size_t)cap * 14 + (size_t)KC1 * 36 +
            E * 12 + E * 4 + (size_t)MS * 12 + (size_t)MAXS * 8 + 64 + 16;
 }
 
@@ -770,8 +793,8 @@ h_finish_kernel(const FinArgs a) {
     extern __shared__ __align__(16) unsigned char fn_smem[];
     const int D = a.ix.D, ML = a.ix.max_len, cap = a.cap, EMAX = MS * ML;
     double *lw = reinterpret_cast<double *>(fn_smem);                     // [ML]
-    float2 *stage = reinterpret_cast<float2 *>(lw + ML);                  // [FN_WARPS][32][33]
-    float *xq = reinterpret_cast<float *>(stage + FN_WARPS * 32 * 33);    // [D]
+    float2 *stage = reinterpret_cast<float2 *>(lw + ML);                  // [FN_WARPS][FN_R][33]
+    float *xq = reinterpret_cast<float *>(stage + FN_WARPS * FN_R * 33);  // [D]
     float *cv = xq + ((D + 3) & ~3);                                      // [cap] candidate a1
     int *cr = reinterpret_cast<int *>(cv + cap);                          // [cap] candidate leaf row
     float *ce = reinterpret_cast<float *>(cr + cap);                      // [cap] candidate error bound E
@@ -806,10 +829,10 @@ h_finish_kernel(const FinArgs a) {
     // exact node scores of the rows list[0..U) with the FP32 path's arithmetic: rows dealt evenly to the warps,
     // lane = row; per 32 attributes a warp reads its rows with coalesced 256-byte loads (all in flight at once and one
     // segment ahead of the arithmetic), transposes them through shared memory, every lane runs its row's chain.
-    // R = rows a warp handles at a time (8, 16 or 32: the loops over rows are unrolled for it).
+    // R = rows a warp handles at a time (8 or FN_R = 16: the loops over rows are unrolled for it).
     auto exact_rows_r = [&](auto rtag, const int *list, int lo, int n_rows, float *outs) {
         constexpr int R = decltype(rtag)::value;
-        float2 *stw = stage + warp * 32 * 33;
+        float2 *stw = stage + warp * FN_R * 33;
         for (int base0 = lo; base0 < lo + n_rows; base0 += R) {
             const int u = base0 + lane;
             const int b = (lane < R && u < lo + n_rows) ? list[u] : -1;
@@ -847,8 +870,7 @@ h_finish_kernel(const FinArgs a) {
         const int lo = warp * per, cnt = max(0, min(per, U - lo));
         if (cnt == 0) return;  // warp-uniform
         if (per <= 8) exact_rows_r(std::integral_constant<int, 8>{}, list, lo, cnt, outs);
-        else if (per <= 16) exact_rows_r(std::integral_constant<int, 16>{}, list, lo, cnt, outs);
-        else exact_rows_r(std::integral_constant<int, 32>{}, list, lo, cnt, outs);
+        else exact_rows_r(std::integral_constant<int, FN_R>{}, list, lo, cnt, outs);  // rounds of FN_R rows
     };
 
     for (long long q = blockIdx.x; q < a.nq; q += gridDim.x) {

@@ -37,7 +37,7 @@ class DenseIndex:
     #            (and an always-on audit sample) go through the exact small-batch path.
     # Batches of up to SMALL_Q queries take the exact small-batch path in every mode (one query: HBM-bound).
     MODES = ("fp32", "fused")
-    FUSED_CAP = 1024              # candidate slots per query of the filtering epilogue
+    FUSED_CAP = 768               # candidate slots per query of the filtering epilogue
     TENSOR_MIN_NODES = 16384      # smaller indexes are answered on the FP32 pipe (launch-bound there; same result)
     EPS_SCALE = 2.0 ** -18        # |fp16x3 ancestor sums - fp32| relative to the operand magnitudes (cw_half.cu eps_of)
     AUDIT_EVERY = 2048            # one query in AUDIT_EVERY is answered again by the exact path and compared (0 = off)
