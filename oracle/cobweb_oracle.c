@@ -46,6 +46,7 @@ typedef struct {
 typedef struct {
     int D;
     int use_info, use_kl, acuity_cutoff;
+    int greedy; /* COBWEB_GREEDY_MODE (src/utils/constants.py:1) */
     float prior_var;
     int n, cap; /* node slots used / allocated */
     int root;
@@ -520,8 +521,9 @@ static int cobweb_one(co_tree *t, const float *x, signed char *trace, long *ntra
             TR(CO_OP_FRINGE);
             return create_new_child(t, nw, x);
         }
-        int b1, b2;
-        int op = best_operation(t, cur, x, &b1, &b2);
+        int b1 = -1, b2 = -1;
+        /* CobwebTorchTree.py:209-213: in greedy mode the action is "new" whatever two_best_children returns */
+        int op = t->greedy ? CO_OP_NEW : best_operation(t, cur, x, &b1, &b2);
         TR(op);
         if (op == CO_OP_BEST) {
             increment_counts(t, cur, x);
@@ -882,3 +884,6 @@ int co_set_threads(int n) {
     return 1;
 #endif
 }
+
+/* COBWEB_GREEDY_MODE switch of the reference (a module constant there, src/utils/constants.py:1). */
+void co_set_greedy(co_tree *t, int greedy) { t->greedy = greedy; }

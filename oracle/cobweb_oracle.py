@@ -100,10 +100,13 @@ def _f32(a):
 class OracleTree:
     """Restates CobwebTorchTree (+ the wrapper's sentence bookkeeping and dense index)."""
 
-    def __init__(self, d, prior_var=None, use_info=True, use_kl=True, acuity_cutoff=False):
+    def __init__(self, d, prior_var=None, use_info=True, use_kl=True, acuity_cutoff=False, greedy=False):
         self.d = int(d)
         self.prior_var = default_prior_var() if prior_var is None else float(prior_var)
         self._h = lib().co_create(self.d, self.prior_var, int(use_info), int(use_kl), int(acuity_cutoff))
+        if greedy:  # COBWEB_GREEDY_MODE = True (src/utils/constants.py)
+            lib().co_set_greedy.argtypes = [C.c_void_p, C.c_int]
+            lib().co_set_greedy(self._h, 1)
         self.n_sentences = 0
         self.leaf_of_sentence = np.zeros(0, dtype=np.int32)  # node slot per sentence id
 

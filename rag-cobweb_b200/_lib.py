@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "libcobweb_b200.so")
 
 CW_E_ARG, CW_E_CAPACITY, CW_E_CUDA, CW_E_FANOUT = -1, -2, -3, -4
-CW_USE_INFO, CW_USE_KL, CW_ACUITY_CUTOFF = 1, 2, 4
+CW_USE_INFO, CW_USE_KL, CW_ACUITY_CUTOFF, CW_GREEDY = 1, 2, 4, 8
 (HDR_ROOT, HDR_N_USED, HDR_FREE_TOP, HDR_POOL_USED, HDR_STATUS, HDR_DONE, HDR_MAX_CHILD, HDR_N_SCORES, _h8, HDR_N_ROWS,
  _h10, HDR_N_LEVELS, _h12) = range(13)
 HDR_WORDS = 16

@@ -7,11 +7,11 @@ Drop-in for the reference's ``src.cobweb`` classes::
 Importing the package never touches CUDA; constructing a tree or wrapper requires a CUDA
 device and the in-tree libcobweb_b200.so (there is no CPU fallback).
 """
-from . import evaluate, serialize, synth, topology  # noqa: F401
+from . import constants, evaluate, serialize, synth, topology  # noqa: F401
 from ._lib import CobwebB200Error  # noqa: F401
 from .tree import CobwebNode, CobwebTorchTree, default_prior_var  # noqa: F401
 from .whitening import PCAICAWhiteningModel  # noqa: F401
 from .wrapper import CobwebWrapper, DenseIndex  # noqa: F401
 
 __all__ = ["CobwebTorchTree", "CobwebWrapper", "CobwebNode", "DenseIndex", "PCAICAWhiteningModel", "CobwebB200Error", "default_prior_var",
-           "synth", "topology", "serialize", "evaluate"]
+           "synth", "topology", "serialize", "evaluate", "constants"]

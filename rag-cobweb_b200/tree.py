@@ -13,7 +13,7 @@ import math
 import numpy as np
 import torch
 
-from . import _lib, serialize, topology
+from . import _lib, constants, serialize, topology
 from .store import NodeStore
 
 OP_NAMES = ["best", "new", "merge", "split", "leaf", "fringe"]
@@ -127,7 +127,9 @@ class CobwebTorchTree:
     IFIT_CHUNK = 32768  # instances per kernel launch (bounds a launch to about a second)
 
     def __init__(self, shape, use_info=True, acuity_cutoff=False, use_kl=True, prior_var=None, alpha=1e-8,
-                 device=None):
+                 device=None, greedy_mode=None):
+        """greedy_mode (additive): None = the module switch constants.COBWEB_GREEDY_MODE at construction time (the
+        reference reads src/utils/constants.py the same way)."""
         _lib.require_cuda()
         if isinstance(shape, torch.Size) or isinstance(shape, (tuple, list)):
             dims = tuple(int(v) for v in shape)
@@ -145,14 +147,18 @@ class CobwebTorchTree:
         self.pi_tensor = torch.tensor(math.pi, dtype=torch.float32, device=self.device)
         pv = default_prior_var() if prior_var is None else float(prior_var)
         self.prior_var = torch.tensor(pv, dtype=torch.float32, device=self.device)
-        flags = (_lib.CW_USE_INFO if self.use_info else 0) | (_lib.CW_USE_KL if self.use_kl else 0) | (
-            _lib.CW_ACUITY_CUTOFF if self.acuity_cutoff else 0)
+        self.greedy_mode = bool(constants.COBWEB_GREEDY_MODE if greedy_mode is None else greedy_mode)
+        flags = self._flags()
         self.store = NodeStore(dims[0], pv, flags, device=self.device)
         self._sent = {}     # node id -> SentenceList
         self._sent_stale = False   # a wrapper added sentences since _sent was built (CobwebWrapper._record)
         self._sent_loader = None
         self._frontier = None
         self.last_trace = None
+
+    def _flags(self):
+        return ((_lib.CW_USE_INFO if self.use_info else 0) | (_lib.CW_USE_KL if self.use_kl else 0) |
+                (_lib.CW_ACUITY_CUTOFF if self.acuity_cutoff else 0) | (_lib.CW_GREEDY if self.greedy_mode else 0))
 
     # ------------------------------------------------------------------ basics
     @property
@@ -364,9 +370,7 @@ class CobwebTorchTree:
         mean, m2 = self.store.rows(b["order"])
         sent = self._sentence_ids_by_node()
         sids = [sent.get(int(n), []) for n in b["order"]]
-        params = dict(use_info=self.use_info, acuity_cutoff=self.acuity_cutoff, use_kl=self.use_kl,
-                      shape=list(self.shape), alpha=self.alpha.item(), prior_var=self.prior_var.item())
-        return serialize.dump_tree_json(params, b["parent"], b["count"], mean, m2, sids)
+        return serialize.dump_tree_json(self._params(), b["parent"], b["count"], mean, m2, sids)
 
     def load_json(self, json_string):
         """CobwebTorchTree.load_json (CobwebTorchTree.py:94-121).  Child order is kept as
@@ -376,13 +380,43 @@ class CobwebTorchTree:
         self.shape = torch.Size(params["shape"])
         self.alpha = torch.tensor(params["alpha"], dtype=torch.float32, device=self.device)
         self.prior_var = torch.tensor(params["prior_var"], dtype=torch.float32, device=self.device)
-        flags = (_lib.CW_USE_INFO if self.use_info else 0) | (_lib.CW_USE_KL if self.use_kl else 0) | (
-            _lib.CW_ACUITY_CUTOFF if self.acuity_cutoff else 0)
-        self.store = NodeStore(self.shape[0], float(self.prior_var.item()), flags, cap=len(parent) + 1024,
+        self.store = NodeStore(self.shape[0], float(self.prior_var.item()), self._flags(), cap=len(parent) + 1024,
                                device=self.device)
         nsent = [len(s) if s else 0 for s in sids]
         self.store.load_arrays(parent, count, nsent, mean, m2)
         self._sent = {i: SentenceList(self, i, s) for i, s in enumerate(sids) if s}
+
+    def _params(self):
+        return dict(use_info=self.use_info, acuity_cutoff=self.acuity_cutoff, use_kl=self.use_kl, shape=list(self.shape),
+                    alpha=self.alpha.item(), prior_var=self.prior_var.item())
+
+    def save_snapshot(self, path, leaf_of_sentence=None, extra=None):
+        """Additive: binary snapshot of the tree (serialize.write_snapshot) -- the same content as dump_json as raw arrays,
+        streamed from the device in row chunks.  leaf_of_sentence: node ids (as returned by ifit) per sentence."""
+        b = self.bfs()
+        order = torch.as_tensor(b["order"].astype(np.int64), device=self.device)
+        pos = np.full(int(b["order"].max()) + 1, -1, np.int64)
+        pos[b["order"]] = np.arange(len(b["order"]))
+
+        def rows(lo, hi):
+            return self.store.mean[order[lo:hi]].cpu().numpy(), self.store.m2[order[lo:hi]].cpu().numpy()
+
+        leaf = None if leaf_of_sentence is None else pos[np.asarray(leaf_of_sentence, np.int64)]
+        serialize.write_snapshot(path, self._params(), b["parent"], b["count"], b["nsent"], rows, leaf, extra)
+
+    def load_snapshot(self, path):
+        """Replace this tree by a snapshot; returns (leaf_of_sentence as node ids of THIS store, extra)."""
+        snap = serialize.read_snapshot(path)
+        p = snap["params"]
+        self.use_info, self.acuity_cutoff, self.use_kl = p["use_info"], p["acuity_cutoff"], p["use_kl"]
+        self.shape = torch.Size(p["shape"])
+        self.alpha = torch.tensor(p["alpha"], dtype=torch.float32, device=self.device)
+        self.prior_var = torch.tensor(p["prior_var"], dtype=torch.float32, device=self.device)
+        n = len(snap["parent"])
+        self.store = NodeStore(self.shape[0], float(self.prior_var.item()), self._flags(), cap=n + 1024, device=self.device)
+        self.store.load_arrays(snap["parent"], snap["count"], snap["n_sent"], snap["mean"], snap["m2"])
+        self._sent, self._sent_stale = {}, False
+        return snap["leaf_of_sentence"], snap["extra"]
 
     def load_arrays(self, parent, count, n_sent, mean, m2):
         """Replace the tree by flat arrays (topologically ordered; see NodeStore.load_arrays)."""

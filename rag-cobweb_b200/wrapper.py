@@ -790,6 +790,46 @@ class CobwebWrapper:
         w._leaf_of_sentence = leaf
         return w
 
+    def save_snapshot(self, path):
+        """Additive: binary snapshot of tree + sentence map + sentences; a 1M-node tree is a few seconds of
+        streaming instead of gigabytes of decimal JSON.  load_snapshot restores an equivalent wrapper."""
+        self.tree.save_snapshot(path, self._leaf_of_sentence,
+                                extra={"sentences": self.sentences if any(s is not None for s in self.sentences) else None,
+                                       "n_sentences": len(self.sentences), "max_init_search": self.max_init_search,
+                                       "level_weights": self._level_weights})
+
+    @staticmethod
+    def load_snapshot(path, encode_func=lambda x: x):
+        w = CobwebWrapper.__new__(CobwebWrapper)
+        w.encode_func, w.device = encode_func, "cuda"
+        w._index, w._weight_schedule, w._schedule_params, w.max_depth = None, None, {}, 0
+        w._shard_key = w._shard_index = None
+        w.tree = CobwebTorchTree(shape=(1,), device=w.device)
+        leaf, extra = w.tree.load_snapshot(path)
+        w._leaf_of_sentence = np.asarray(leaf, np.int32)
+        w.sentences = extra.get("sentences") or [None] * int(extra.get("n_sentences", len(leaf)))
+        w.max_init_search = extra.get("max_init_search", 100000)
+        w._level_weights = extra.get("level_weights")
+        w.tree._sent_stale, w.tree._sent_loader = True, w._load_sentence_lists
+        return w
+
+    def get_node_path_stats(self, sentence_id):
+        """CobwebWrapper.get_node_path_stats (CobwebWrapper.py:297-313): (means [len, D], vars [len, D]) of the nodes on
+        the root -> leaf path of a sentence, root first; (None, None) for an unknown sentence."""
+        if not 0 <= sentence_id < len(self._leaf_of_sentence) or self._leaf_of_sentence[sentence_id] < 0:
+            return None, None
+        node, path = int(self._leaf_of_sentence[sentence_id]), []
+        par = self.tree.store.parent
+        while node >= 0:
+            path.append(node)
+            node = int(par[node].item())
+        idx = torch.as_tensor(path[::-1], device=self.tree.device)
+        st = self.tree.store
+        cnt = st.count[idx].unsqueeze(1)
+        var = torch.where(cnt > 0, self.tree.compute_var(st.m2[idx], cnt.clamp_min(1e-30)),
+                          self.tree.prior_var.expand_as(st.m2[idx]))
+        return st.mean[idx].clone(), var
+
     def visualize_subtrees(self, directory, num_leaves=6):
         raise NotImplementedError("graphviz rendering is outside the hot-path scope (SURVEY.md section 2, row 3)")
 

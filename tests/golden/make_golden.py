@@ -200,7 +200,8 @@ def run_case(name, n, d, kind, nq, k):
 
 
 if __name__ == "__main__":
-    names = [a for a in sys.argv[1:] if a != "whitening"] or ([] if "whitening" in sys.argv[1:] else list(CASES))
+    extra = ("whitening", "greedy", "json")
+    names = [a for a in sys.argv[1:] if a not in extra] or ([] if any(a in extra for a in sys.argv[1:]) else list(CASES))
     for nm in names:
         run_case(nm, *CASES[nm])
 
@@ -227,3 +228,53 @@ def run_whitening_case():
 
 if "whitening" in sys.argv[1:]:
     run_whitening_case()
+
+
+def run_greedy_case():
+    """COBWEB_GREEDY_MODE = True (src/utils/constants.py): the reference's ifit takes "new" at every internal node
+    (CobwebTorchTree.py:209-213).  Records the resulting tree for 150 x 24 unit rows with 10 duplicated rows."""
+    synth = load_synth()
+    Node, Tree, Wrapper = import_reference()
+    import src.cobweb.CobwebTorchNode as node_mod
+    import src.cobweb.CobwebTorchTree as tree_mod
+    node_mod.COBWEB_GREEDY_MODE = tree_mod.COBWEB_GREEDY_MODE = True
+    try:
+        x = synth.corpus(150, 24, "unit", seed=0)
+        x[40:50] = x[5:15]
+        t = Tree((24,), device="cpu")
+        for row in x:
+            t.ifit(torch.tensor(row))
+        order, parent = bfs(t.root)
+        out = os.path.join(HERE, "greedy_unit_150x24.npz")
+        np.savez_compressed(out, bfs_parent=parent, bfs_count=np.asarray([float(n.count) for n in order], np.float32),
+                            bfs_nchild=np.asarray([len(n.children) for n in order], np.int32),
+                            mean=np.stack([n.mean.numpy() for n in order]).astype(np.float32),
+                            m2=np.stack([n.meanSq.numpy() for n in order]).astype(np.float32))
+        print(f"greedy: nodes={len(order)} root children={len(t.root.children)} -> {out}")
+    finally:
+        node_mod.COBWEB_GREEDY_MODE = tree_mod.COBWEB_GREEDY_MODE = False
+
+
+def run_json_case():
+    """The reference's own wire format: CobwebTorchTree.dump_json (CobwebTorchTree.py:67-81) of an 80 x 12 tree whose
+    leaves carry sentence ids, written verbatim to reference_tree_80x12.json, plus what the reference answers on it
+    (rank scores of 6 queries) so that load -> predict can be checked against the reference."""
+    synth = load_synth()
+    Node, Tree, Wrapper = import_reference()
+    x = synth.corpus(80, 12, "unit", seed=0)
+    x[30:33] = x[4]
+    w = Wrapper(corpus=[f"s{i}" for i in range(80)], corpus_embeddings=x, encode_func=lambda s: s)
+    doc = w.tree.dump_json()
+    with open(os.path.join(HERE, "reference_tree_80x12.json"), "w") as f:
+        f.write(doc)
+    q, _ = synth.queries(x, 6, "unit", seed=1)
+    rank = np.stack([w.cobweb_rank_scores(torch.tensor(qq), is_embedding=True).detach().numpy() for qq in q]).astype(np.float32)
+    np.savez_compressed(os.path.join(HERE, "reference_tree_80x12_answers.npz"), rank_scores=rank,
+                        leaf_count=np.asarray([float(w.sentence_to_node[i].count) for i in range(80)], np.float32))
+    print(f"json: {len(doc)} bytes, rank scores {rank.shape}")
+
+
+if "greedy" in sys.argv[1:]:
+    run_greedy_case()
+if "json" in sys.argv[1:]:
+    run_json_case()

@@ -690,3 +690,103 @@ def test_fused_predict_small_and_odd_shapes():
     assert ix.hx["leaf_layout"] == 2
     a, b, _ = ix.predict(qd, k)
     assert torch.equal(a, ids32) and torch.equal(b, v32) and ix.stats["audit_mismatch"] == 0
+
+
+def test_ifit_greedy_mode(golden_dir):
+    """COBWEB_GREEDY_MODE (src/utils/constants.py; CobwebTorchTree.py:209-213): the kernel takes "new" at every internal
+    node.  Equal to the reference's recorded tree, and to the oracle beyond the scoring lists' fan-out limit (the flat
+    tree's root has one child per instance)."""
+    from rag_cobweb_b200 import constants
+    g = np.load(os.path.join(golden_dir, "greedy_unit_150x24.npz"))
+    x = synth.corpus(150, 24, "unit", seed=0)
+    x[40:50] = x[5:15]
+    constants.COBWEB_GREEDY_MODE = True
+    try:
+        tree = CobwebTorchTree((24,))          # reads the module switch like the reference does
+    finally:
+        constants.COBWEB_GREEDY_MODE = False
+    assert tree.greedy_mode and not CobwebTorchTree((24,)).greedy_mode
+    tree.ifit_batch(x)
+    b = tree.bfs()
+    mean, m2 = tree.store.rows(b["order"])
+    assert np.array_equal(b["parent"], g["bfs_parent"]) and np.array_equal(b["count"], g["bfs_count"])
+    assert np.array_equal(mean, g["mean"]) and np.array_equal(m2, g["m2"])
+    n, d = 3000, 16
+    x = synth.corpus(n, d, "whitened", seed=2)
+    tree, ref = CobwebTorchTree((d,), greedy_mode=True), OracleTree(d, greedy=True)
+    leaves = tree.ifit_batch(x, tag_sentences=True).cpu().numpy()
+    assert_same_tree(tree, ref, leaves, ref.ifit(x))
+    assert tree.bfs()["nchild"][0] == n - 1 > 2048
+
+
+def test_reference_json_fixture_and_snapshot(golden_dir, tmp_path):
+    """A document written by the REFERENCE's dump_json (fixture): load -> the reference's own rank scores (2e-5), re-dump
+    byte-identical; binary snapshot of the same wrapper: load -> identical answers."""
+    import json
+    doc = open(os.path.join(golden_dir, "reference_tree_80x12.json")).read()
+    ans = np.load(os.path.join(golden_dir, "reference_tree_80x12_answers.npz"))
+    w = CobwebWrapper.load_json(json.dumps({"tree": json.loads(doc), "sentences": [f"s{i}" for i in range(80)],
+                                            "embedding_dim": 12}))
+    assert w.tree.dump_json() == doc
+    x = synth.corpus(80, 12, "unit", seed=0)
+    x[30:33] = x[4]
+    q, _ = synth.queries(x, 6, "unit", seed=1)
+    got = w.rank_scores_batch(q).cpu().numpy()
+    np.testing.assert_allclose(got, ans["rank_scores"], rtol=2e-5, atol=1e-5)
+    assert [float(w.sentence_to_node[i].count) for i in range(80)] == ans["leaf_count"].tolist()
+    # reading .sentence_id on a handle must not disturb later dumps / predicts (round-1 advisor finding)
+    assert sorted(w.sentence_to_node[4].sentence_id) == [4, 30, 31, 32] or 4 in w.sentence_to_node[4].sentence_id
+    ids0, v0 = w.predict_fast_batch(q, 5)
+    means, vars_ = w.get_node_path_stats(7)
+    assert means.shape == vars_.shape and means.shape[1] == 12 and w.get_node_path_stats(10 ** 6) == (None, None)
+    path = str(tmp_path / "w.cwb")
+    w.save_snapshot(path)
+    w2 = CobwebWrapper.load_snapshot(path)
+    assert w2.sentences == w.sentences and w2.tree.dump_json() == doc
+    ids1, v1 = w2.predict_fast_batch(q, 5)
+    assert torch.equal(ids0, ids1) and torch.equal(v0, v1)
+    assert w2.cobweb_predict(q[0], k=3, return_ids=True, is_embedding=True) == w.cobweb_predict(q[0], k=3, return_ids=True, is_embedding=True)
+    # a wrapper built here: .sentence_id before and after adding sentences, JSON and snapshot agree
+    w3 = CobwebWrapper(corpus=[f"t{i}" for i in range(40)], corpus_embeddings=x[:40])
+    assert w3.sentence_to_node[0].sentence_id == [0]
+    w3.add_sentences([f"t{i}" for i in range(40, 80)], x[40:])
+    assert 79 in w3.sentence_to_node[79].sentence_id and len(w3.cobweb_predict(q[0], k=3, return_ids=True, is_embedding=True)) >= 3
+    w4 = CobwebWrapper.load_json(w3.dump_json())
+    assert np.array_equal(w4._leaf_of_sentence >= 0, np.ones(80, bool)) and w4.tree.dump_json() == w3.tree.dump_json()
+    w3.add_sentences(["x", "y", "z"], x[:2])   # more sentences than vectors: the reference zips (CobwebWrapper.py:70)
+    assert len(w3) == 82 and len(w3._leaf_of_sentence) == 82
+
+
+@pytest.mark.parametrize("name", ["cfg1_unit_1000x384", "cfg2_unit_1500x1024"])
+def test_baseline_configs_vs_oracle(golden_dir, name):
+    """BASELINE configs[0] (1,000 x 384) and configs[1] (1,500 x 1024) at full size: ifit traces / trees / statistics
+    bit-exact against the oracle, best-first retrieval identical, dense scores within 1e-5; and the reference's OWN tree
+    (fixture decisions replayed) queried by the engine returns the reference's recorded node scores."""
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    n, d, kind, k = int(g["n"]), int(g["d"]), str(g["kind"]), int(g["k"])
+    x = synth.corpus(n, d, kind, seed=0)
+    tree, ref = CobwebTorchTree((d,)), OracleTree(d)
+    leaves, ops, offs = tree.ifit_batch(x, tag_sentences=True, trace=True)
+    rl, rops, roffs = ref.ifit(x, trace=True)
+    assert np.array_equal(ops, rops) and np.array_equal(offs, roffs)
+    pos, rpos = assert_same_tree(tree, ref, leaves.cpu().numpy(), rl)
+    q, _ = synth.queries(x, 64, kind, seed=1)
+    r = tree.categorize_batch(q, retrieve_k=k, max_nodes=100000)
+    cl, _, _, cc = ref.categorize(q, k=k, max_nodes=100000)
+    assert np.array_equal(pos[r["leaves"].cpu().numpy()], rpos[cl]) and np.array_equal(r["lp_calls"].cpu().numpy(), cc)
+    # the reference's tree: guided replay -> engine store -> node scores vs the reference's recorded ones
+    ref2 = OracleTree(d)
+    dec = g["ops"][g["ops"] < 4]
+    l2, _, _ = ref2.ifit_guided(x, dec, g["dec_b1"], g["dec_b2"])
+    rb = ref2.bfs()
+    mean, m2 = ref2.rows(rb["order"])
+    w = CobwebWrapper(corpus=[None], corpus_embeddings=x[:1])
+    w.tree.load_arrays(rb["parent"], rb["count"], rb["nsent"], mean, m2)
+    p2 = pos_of(rb)
+    w.sentences, w._leaf_of_sentence = [None] * n, p2[l2].astype(np.int32)
+    w._invalidate_prediction_index()
+    w.build_prediction_index()
+    qg, _ = synth.queries(x, g["rank_scores"].shape[0], kind, seed=1)
+    ns = w._index.node_scores(torch.from_numpy(qg).cuda()).cpu().numpy()
+    np.testing.assert_allclose(ns, g["node_scores"], rtol=1e-5, atol=1e-4)
+    np.testing.assert_allclose(w.rank_scores_batch(qg).cpu().numpy(), g["rank_scores"], rtol=2e-5, atol=1e-4)

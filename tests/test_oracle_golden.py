@@ -138,3 +138,42 @@ def test_load_roundtrip(golden_dir):
     lv1, _, _, c1 = t.categorize(q, k=5)
     lv2, _, _, c2 = t2.categorize(q, k=5)
     assert np.array_equal(bfs_pos(b)[lv1], lv2) and np.array_equal(c1, c2)
+
+
+def test_oracle_greedy_mode_matches_reference(golden_dir):
+    """COBWEB_GREEDY_MODE = True (src/utils/constants.py; CobwebTorchTree.py:209-213): "new" at every internal node.
+    Fixture recorded by running the reference with the switch on (make_golden.py greedy)."""
+    g = np.load(os.path.join(golden_dir, "greedy_unit_150x24.npz"))
+    x = synth.corpus(150, 24, "unit", seed=0)
+    x[40:50] = x[5:15]
+    t = OracleTree(24, greedy=True)
+    t.ifit(x)
+    b = t.bfs()
+    assert np.array_equal(b["parent"], g["bfs_parent"]) and np.array_equal(b["count"], g["bfs_count"])
+    assert np.array_equal(b["nchild"], g["bfs_nchild"]) and b["depth"].max() == 1   # a flat tree: no duplicate is matched
+    mean, m2 = t.rows(b["order"])
+    assert np.array_equal(mean, g["mean"]) and np.array_equal(m2, g["m2"])
+
+
+def test_reference_json_document_roundtrip(golden_dir):
+    """The reference's own dump_json output (fixture written by make_golden.py json): load_tree_json -> dump_tree_json
+    reproduces the document byte for byte (fp32 -> shortest decimal -> fp32 is lossless), and the binary snapshot
+    carries the same content."""
+    from rag_cobweb_b200 import serialize
+    doc = open(os.path.join(golden_dir, "reference_tree_80x12.json")).read()
+    params, parent, count, mean, m2, sids = serialize.load_tree_json(doc)
+    assert serialize.dump_tree_json(params, parent, count, mean, m2, sids) == doc
+    assert len(parent) == 112 and sorted(s for l in sids for s in l) == list(range(80))
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "t.cwb")
+        leaf = np.zeros(80, np.int32)
+        for node, l in enumerate(sids):
+            for s in l:
+                leaf[s] = node
+        serialize.write_snapshot(path, params, parent, count, [len(l) for l in sids], lambda lo, hi: (mean[lo:hi], m2[lo:hi]),
+                                 leaf, extra={"n_sentences": 80})
+        snap = serialize.read_snapshot(path)
+        assert snap["params"] == params and np.array_equal(snap["parent"], parent) and np.array_equal(snap["count"], count)
+        assert np.array_equal(snap["mean"], mean) and np.array_equal(snap["m2"], m2) and np.array_equal(snap["leaf_of_sentence"], leaf)
+        assert os.path.getsize(path) < 0.3 * len(doc)
