@@ -171,8 +171,10 @@ class NodeStore:
         within = np.arange(len(order)) - np.repeat(np.cumsum(cnt) - cnt, cnt)
         pool[off[par_sorted] + within] = order
         dev = self.device
-        self.mean[:n] = torch.as_tensor(np.ascontiguousarray(mean, np.float32), device=dev)
-        self.m2[:n] = torch.as_tensor(np.ascontiguousarray(m2, np.float32), device=dev)
+        for lo in range(0, n, 1 << 16):  # in row chunks: the sources may be memory-mapped snapshots of many GB
+            hi = min(n, lo + (1 << 16))
+            self.mean[lo:hi] = torch.from_numpy(np.array(mean[lo:hi], dtype=np.float32, copy=True)).to(dev)
+            self.m2[lo:hi] = torch.from_numpy(np.array(m2[lo:hi], dtype=np.float32, copy=True)).to(dev)
         self.count[:n] = torch.as_tensor(np.asarray(count, np.float32), device=dev)
         self.parent[:n] = torch.as_tensor(parent.astype(np.int32), device=dev)
         self.child_off[:n] = torch.as_tensor(off.astype(np.int32), device=dev)

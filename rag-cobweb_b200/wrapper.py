@@ -20,7 +20,7 @@ import os
 import numpy as np
 import torch
 
-from . import _lib, topology
+from . import _lib, topology, topology_device
 from .tree import CobwebNode, CobwebTorchTree
 
 
@@ -49,19 +49,25 @@ class DenseIndex:
         L = _lib.load()
         self.tree = tree
         dev = tree.device
-        t = tree.store.topology()
-        order, parent_b, depth = topology.bfs_order(t["root"], t["child_off"], t["child_cnt"], t["child_pool"])
-        leaf_of_sentence = np.asarray(leaf_of_sentence)
-        if len(leaf_of_sentence) and int(leaf_of_sentence.min()) < 0:
+        # topology on the device (topology_device.py mirrors the numpy statements in topology.py): the store's arrays
+        # are not copied to the host, so the index is rebuilt after add_sentences in milliseconds
+        st = tree.store
+        h = st.header()
+        n_used, root = int(h[_lib.HDR_N_USED]), int(h[_lib.HDR_ROOT])
+        order, parent_b, depth = topology_device.bfs_order(root, st.child_off, st.child_cnt, st.child_pool)
+        leaf_np = np.asarray(leaf_of_sentence)
+        if len(leaf_np) and int(leaf_np.min()) < 0:
             raise ValueError("a sentence has no leaf (leaf_of_sentence < 0): the sentence list and the tree do not match")
         self.sentence_ids = None
         if sentence_ids is not None:
+            # a shard of the sentences: only the nodes on their paths are indexed (host statement; built once per shard)
             self.sentence_ids = np.asarray(sentence_ids, np.int64)
-            leaf_of_sentence = leaf_of_sentence[self.sentence_ids]
-            order, parent_b, depth = topology.restrict_to_paths(order, parent_b, depth, leaf_of_sentence, t["n_used"])
-        self.order_host = order
-        self._topo = (parent_b, depth, leaf_of_sentence, level_weights, t["n_used"])
-        self.nn = len(order)
+            leaf_np = leaf_np[self.sentence_ids]
+            o, p_, d_ = topology.restrict_to_paths(order.cpu().numpy(), parent_b.cpu().numpy(), depth.cpu().numpy(), leaf_np, n_used)
+            order, parent_b, depth = (torch.as_tensor(a_, device=dev) for a_ in (o, p_, d_))
+        leaf_dev = torch.as_tensor(leaf_np.astype(np.int64), device=dev)
+        self._topo = (order, parent_b, depth, leaf_dev, level_weights, n_used)
+        self.nn = int(order.numel())
         self.max_depth = int(depth.max()) + 1
         d = tree.d
         self.n_ntiles = (self.nn + _lib.TILE_N - 1) // _lib.TILE_N
@@ -71,22 +77,22 @@ class DenseIndex:
         self.R = torch.empty(tile_elems, dtype=torch.float32, device=dev)
         self.MB = torch.empty(tile_elems, dtype=torch.float32, device=dev)
         self.sumlog = torch.zeros(self.ld, dtype=torch.float32, device=dev)
-        self.order = torch.as_tensor(order.astype(np.int32), device=dev)
-        self.n_pos = len(leaf_of_sentence)
+        self.order = order.to(torch.int32)
+        self.n_pos = int(leaf_dev.numel())
         ix = _lib.CwIndex()
         ix.D, ix.nn, ix.n_ntiles, ix.n_ktiles = d, self.nn, self.n_ntiles, self.n_ktiles
         ix.R, ix.MB, ix.sumlog = self.R.data_ptr(), self.MB.data_ptr(), self.sumlog.data_ptr()
         if self.n_pos:
-            p = topology.sentence_paths(order, parent_b, depth, leaf_of_sentence, level_weights, n_slots=t["n_used"])
+            p = topology_device.sentence_paths(order, parent_b, depth, leaf_dev, level_weights, n_slots=n_used)
             self.max_len = p["max_len"]
-            self.path_idx = torch.as_tensor(np.ascontiguousarray(p["path_idx"].T), device=dev)  # [n_pos, max_len]
-            self.level_w = torch.as_tensor(p["level_w"], dtype=torch.float64, device=dev)
+            self.path_idx = p["path_idx"]  # [n_pos, max_len]
             self._level_w_host = np.asarray(p["level_w"], np.float64)
-            self._pos_leaf_row = p["pos_rec"][:, 2].copy()   # ascending: positions are sorted by leaf row
-            self._path_lens = np.unique(p["pos_rec"][:, 0])
-            if self.sentence_ids is not None:
-                p["pos_rec"][:, 3] = self.sentence_ids[p["pos_rec"][:, 3]]  # local position ids -> global ids
-            self.pos_rec = torch.as_tensor(p["pos_rec"], device=dev)  # [n_pos, 4]
+            self.level_w = torch.as_tensor(self._level_w_host, dtype=torch.float64, device=dev)
+            self._pos_leaf_row = p["pos_leaf_row"]   # ascending: positions are sorted by leaf row
+            self._path_lens = np.asarray(p["path_lens"], np.int64)
+            self.pos_rec = p["pos_rec"]  # [n_pos, 4]
+            if self.sentence_ids is not None:  # local position ids -> global ids
+                self.pos_rec[:, 3] = torch.as_tensor(self.sentence_ids, device=dev)[self.pos_rec[:, 3].long()].to(torch.int32)
             ix.n_pos, ix.max_len = self.n_pos, self.max_len
             ix.path_idx, ix.pos_rec, ix.level_w = self.path_idx.data_ptr(), self.pos_rec.data_ptr(), self.level_w.data_ptr()
         self.ix = ix
@@ -125,15 +131,14 @@ class DenseIndex:
         """Operands of the fused mode: fp16 operand sets for the internal rows (hi + lo) and the leaf rows (hi), per-leaf
         records, row-major {r, mb} rows for the exact arithmetic, the constants of eps (topology.fused_layout)."""
         L, dev, d = _lib.load(), self.tree.device, self.tree.d
-        parent_b, depth, leaf_of_sentence, level_weights, n_used = self._topo
-        F = topology.fused_layout(self.order_host, parent_b, depth, leaf_of_sentence, level_weights, n_slots=n_used,
-                                  sentence_ids=self.sentence_ids, tile=_lib.H_TILE)
+        order, parent_b, depth, leaf_dev, level_weights, n_used = self._topo
+        F = topology_device.fused_layout(order, parent_b, depth, leaf_dev, level_weights, n_slots=n_used,
+                                         sentence_ids=None if self.sentence_ids is None else torch.as_tensor(self.sentence_ids, device=dev),
+                                         tile=_lib.H_TILE)
         st, store = _lib.stream_ptr(), self.tree.store.struct()
-        n_int, n_leaf = len(F["int_rows"]), len(F["leaf_rows"])
+        n_int, n_leaf = int(F["int_rows"].numel()), int(F["leaf_rows"].numel())
         hx = {"F": F, "n_int": n_int, "n_leaf": n_leaf, "n_s": int(F["n_sample_tiles"])}
-        i32 = lambda a: torch.as_tensor(np.ascontiguousarray(a, np.int32), device=dev)
-        f32 = lambda a: torch.as_tensor(np.ascontiguousarray(a, np.float32), device=dev)
-        hx["leaf_rows"] = i32(F["leaf_rows"])
+        hx["leaf_rows"] = F["leaf_rows"]
         flag = torch.zeros(1, dtype=torch.int32, device=dev)
         iso = L.cw_h_rows_isotropic(store, self.order.data_ptr(), hx["leaf_rows"].data_ptr(), n_leaf, flag.data_ptr(), st)
         if iso < 0:
@@ -156,15 +161,15 @@ class DenseIndex:
         fi.ix = self.ix
         fi.n_int, fi.n_leaf, fi.n_sample_tiles = n_int, n_leaf, hx["n_s"]
         if n_int:
-            hx["int_rows"] = i32(F["int_rows"])
+            hx["int_rows"] = F["int_rows"]
             fi.internal, hx["B_int"], hx["rc_int"] = hset(hx["int_rows"], n_int, _lib.H_F2, 3, None)
-            hx["int_parent"], hx["int_w"], hx["level_off"] = i32(F["int_parent"]), f32(F["int_w"]), i32(F["level_off"])
+            hx["int_parent"], hx["int_w"], hx["level_off"] = F["int_parent"], F["int_w"], F["level_off"]
             fi.int_parent, fi.int_w, fi.level_off = hx["int_parent"].data_ptr(), hx["int_w"].data_ptr(), hx["level_off"].data_ptr()
-            fi.n_levels = len(F["level_off"]) - 1
-        hx["leaf_aux"] = [f32(F["leaf_w"]), f32(F["leaf_inv_len"]), i32(F["leaf_parent"]), i32(F["leaf_len"])]
+            fi.n_levels = int(F["level_off"].numel()) - 1
+        hx["leaf_aux"] = [F["leaf_w"], F["leaf_inv_len"], F["leaf_parent"], F["leaf_len"]]
         fi.leaves, hx["B_leaf"], hx["rc_leaf"] = hset(hx["leaf_rows"], n_leaf, hx["leaf_layout"], 1, hx["leaf_aux"])
-        hx["leaf_pos"] = i32(np.searchsorted(self._pos_leaf_row, F["leaf_rows"]))
-        hx["sent_off"], hx["sent_ids"] = i32(F["sent_off"]), i32(F["sent_ids"])
+        hx["leaf_pos"] = torch.searchsorted(self._pos_leaf_row, F["leaf_rows"].to(torch.int64)).to(torch.int32)
+        hx["sent_off"], hx["sent_ids"] = F["sent_off"], F["sent_ids"]
         fi.leaf_row_b, fi.leaf_pos = hx["leaf_rows"].data_ptr(), hx["leaf_pos"].data_ptr()
         fi.sent_off, fi.sent_ids = hx["sent_off"].data_ptr(), hx["sent_ids"].data_ptr()
         # row-major {r, mb} rows: the operands of the exact arithmetic in the finish kernel

@@ -716,7 +716,7 @@ def test_ifit_greedy_mode(golden_dir):
     tree, ref = CobwebTorchTree((d,), greedy_mode=True), OracleTree(d, greedy=True)
     leaves = tree.ifit_batch(x, tag_sentences=True).cpu().numpy()
     assert_same_tree(tree, ref, leaves, ref.ifit(x))
-    assert tree.bfs()["nchild"][0] == n - 1 > 2048
+    assert tree.bfs()["nchild"][0] == n > 2048
 
 
 def test_reference_json_fixture_and_snapshot(golden_dir, tmp_path):

@@ -347,3 +347,48 @@ def test_fused_mode_host_policy():
         warnings.simplefilter("always")
         ix._account(st)
     assert ix.stats["audit_mismatch"] == 1 and ix.eps_scale == 4 * DenseIndex.EPS_SCALE and len(rec) == 1
+
+
+def test_device_topology_matches_host_topology():
+    """topology_device (torch ops on the store's tensors) == topology (numpy statements) on random trees:
+    BFS numbering, per-sentence paths / position records, fused layout -- with level weights, leaves holding several
+    sentences, shuffled child pools and dead slots."""
+    from rag_cobweb_b200 import topology_device as td
+    rng = np.random.default_rng(11)
+    for n_nodes, lw, tile, every in ((1, None, 64, 4), (50, None, 16, 2), (3000, [1.0, 0.5, 2.0, 1.5], 64, 4), (2500, None, 64, 8)):
+        parent = np.full(n_nodes, -1, np.int64)
+        for i in range(1, n_nodes):
+            parent[i] = rng.integers(max(0, i - 40), i)
+        child_cnt = np.bincount(parent[1:], minlength=n_nodes).astype(np.int32)
+        # child lists at scattered pool offsets (lists are allocated with slack and out of order in the real store)
+        caps = child_cnt + rng.integers(0, 3, n_nodes).astype(np.int32)
+        perm = rng.permutation(n_nodes)
+        off = np.zeros(n_nodes, np.int64)
+        off[perm] = np.cumsum(caps[perm]) - caps[perm]
+        pool = np.full(int(caps.sum()) + 1, -7, np.int32)
+        fill = np.zeros(n_nodes, np.int64)
+        for i in range(1, n_nodes):
+            p = parent[i]
+            pool[off[p] + fill[p]] = i
+            fill[p] += 1
+        child_off = off.astype(np.int32)
+        order, parent_b, depth = topology.bfs_order(0, child_off, child_cnt, pool)
+        t = lambda a: torch.as_tensor(a)
+        o2, p2, d2 = td.bfs_order(0, t(child_off), t(child_cnt), t(pool))
+        assert np.array_equal(o2.numpy(), order) and np.array_equal(p2.numpy(), parent_b) and np.array_equal(d2.numpy(), depth)
+        leaves = np.nonzero(child_cnt == 0)[0]
+        los = np.concatenate([leaves, leaves[: len(leaves) // 7], leaves[:3]])
+        los = los[rng.permutation(len(los))]
+        P = topology.sentence_paths(order, parent_b, depth, los, lw, n_slots=n_nodes)
+        P2 = td.sentence_paths(o2, p2, d2, t(los), lw, n_slots=n_nodes)
+        assert P2["max_len"] == P["max_len"] and np.array_equal(P2["path_idx"].numpy(), P["path_idx"].T)
+        assert np.array_equal(P2["pos_rec"].numpy(), P["pos_rec"]) and np.allclose(P2["level_w"], P["level_w"])
+        assert np.array_equal(P2["pos_leaf_row"].numpy(), P["pos_rec"][:, 2]) and P2["path_lens"] == np.unique(P["pos_rec"][:, 0]).tolist()
+        if n_nodes == 1:
+            continue
+        F = topology.fused_layout(order, parent_b, depth, los, lw, n_slots=n_nodes, tile=tile, sample_every=every)
+        F2 = td.fused_layout(o2, p2, d2, t(los), lw, n_slots=n_nodes, tile=tile, sample_every=every)
+        for key in ("int_rows", "int_parent", "int_w", "level_off", "leaf_rows", "leaf_parent", "leaf_w", "leaf_inv_len", "leaf_len",
+                    "sent_off", "sent_ids"):
+            assert np.array_equal(F2[key].numpy(), np.asarray(F[key])), (n_nodes, key)
+        assert F2["n_sample_tiles"] == F["n_sample_tiles"] and F2["max_len"] == F["max_len"]
