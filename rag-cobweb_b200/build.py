@@ -34,7 +34,7 @@ def nvcc():
 
 def sources():
     out = [os.path.join(CSRC, u) for u, _ in UNITS]
-    out += [os.path.join(CSRC, "cw_common.cuh"), os.path.join(os.path.dirname(HERE), "include", "cobweb_b200.h")]
+    out += [os.path.join(CSRC, "cw_common.cuh"), os.path.join(CSRC, "cw_nvtx.h"), os.path.join(os.path.dirname(HERE), "include", "cobweb_b200.h")]
     return out
 
 

@@ -18,6 +18,7 @@
 #include <stdint.h>
 
 #include "../../include/cobweb_b200.h"
+#include "cw_nvtx.h"
 
 void cw_set_error(const char *fmt, ...);
 int cw_check_cuda(cudaError_t e, const char *what);
@@ -594,6 +595,7 @@ extern "C" int64_t cw_score_ldq(int64_t nq) { return (nq + TQ - 1) / TQ * TQ; }
 
 extern "C" int cw_dense_node_scores(const cw_index *ix, const float *Q, int64_t nq, float *xt_scratch,
                                     float *node_scores, int64_t ldq, void *stream) {
+    CwRange range("cw_dense_node_scores");
     if (!ix || !Q || !node_scores || !xt_scratch || nq < 0 || ldq < cw_score_ldq(nq) || (ldq & 3)) {
         cw_set_error("cw_dense_node_scores: bad argument (ldq must be >= cw_score_ldq(nq) and a multiple of 4)");
         return CW_E_ARG;
@@ -688,6 +690,7 @@ static int paths_topk_launch(const cw_index *ix, const float *node_scores, int64
 extern "C" int cw_dense_paths_topk(const cw_index *ix, const float *node_scores, int64_t ldq, int64_t nq, int k,
                                    float *leaf_scores, int32_t *out_sid, float *out_score, int32_t *scratch,
                                    void *stream) {
+    CwRange range("cw_dense_paths_topk");
     if (ldq < cw_score_ldq(nq)) {
         cw_set_error("cw_dense_paths_topk: ldq must be >= cw_score_ldq(nq)");
         return CW_E_ARG;
@@ -698,6 +701,7 @@ extern "C" int cw_dense_paths_topk(const cw_index *ix, const float *node_scores,
 // One call = batched cobweb_predict_fast(return_ids=True) on HOST buffers with the FP32 form
 extern "C" int cw_predict_dense_host(const cw_index *ix, const cw_dense_work *w, const float *Q_host, int64_t nq, int k,
                                      int32_t *out_sid_host, float *out_score_host, void *stream) {
+    CwRange range("cw_predict_dense_host");
     if (!ix || !Q_host || !w || !w->Q_dev || !w->xt_scratch || !w->node_scores || !w->out_sid_dev || !w->out_score_dev ||
         !w->scratch || !out_sid_host || !out_score_host || k < 1 || nq < 0) {
         cw_set_error("cw_predict_dense_host: bad argument");
@@ -846,6 +850,7 @@ extern "C" int64_t cw_small_scratch_words(int64_t n_pos, int k) {
 int cw_small_predict_impl(const cw_index *ix, const float *Q, int64_t nq, const int32_t *which, const int32_t *n_dev,
                           int32_t which_off, int scatter, int k, float *sm_Q, float *sm_scores, int32_t *sm_scratch, int32_t *sm_sid,
                           float *sm_val, int32_t *sm_n, int32_t *out_sid, float *out_val, cudaStream_t st) {
+    CwRange range("cw_small_predict");
     if (!ix || !Q || nq < 0 || nq > CW_SMALL_Q || k < 1 || k > CW_MAX_K || !sm_scores || !sm_scratch || !out_sid || !out_val ||
         (which && (!sm_Q || !sm_sid || !sm_val || !sm_n)) || (n_dev && !which)) {
         cw_set_error("cw_small_predict: bad argument (nq=%lld, at most %d; k=%d)", (long long)nq, CW_SMALL_Q, k);
@@ -906,6 +911,7 @@ extern "C" int cw_small_predict(const cw_index *ix, const float *Q, int64_t nq, 
 extern "C" int cw_small_predict_host(const cw_index *ix, const float *Q_host, int64_t nq, int k, float *sm_Q, float *sm_scores,
                                      int32_t *sm_scratch, int32_t *sm_sid, float *sm_val, int32_t *sm_n, int32_t *out_sid_host,
                                      float *out_val_host, void *stream) {
+    CwRange range("cw_small_predict_host");
     if (!ix || !Q_host || !sm_Q || !sm_sid || !sm_val || !out_sid_host || !out_val_host || nq < 0 || nq > CW_SMALL_Q) {
         cw_set_error("cw_small_predict_host: bad argument");
         return CW_E_ARG;

@@ -33,6 +33,7 @@
 #include <type_traits>
 
 #include "../../include/cobweb_b200.h"
+#include "cw_nvtx.h"
 
 void cw_set_error(const char *fmt, ...);
 int cw_check_cuda(cudaError_t e, const char *what);
@@ -1152,7 +1153,17 @@ int cw_small_predict_impl(const cw_index *ix, const float *Q, int64_t nq, const 
 // ev (optional): CW_FUSED_STAGES + 1 events recorded at the stage boundaries (cw_fused_profile)
 static int fused_chunk(const cw_fused_index *fi, const cw_fused_work *w, const float *Q, int64_t nq, int k, int32_t *out_sid,
                        float *out_val, cudaStream_t st, cudaEvent_t *ev = nullptr) {
-    auto mark = [&](int i) { if (ev) cudaEventRecord(ev[i], st); };
+    CwRange range("cw_fused_chunk");
+    static const char *const stage_names[CW_FUSED_STAGES] = {"query_operands", "internal_scores", "cumulative_sums", "sample_threshold",
+                                                              "leaf_filter", "finish", "fallback_audit"};
+    int open_stage = -1;
+    auto mark = [&](int i) {
+        if (ev) cudaEventRecord(ev[i], st);
+        if (open_stage >= 0) nvtxRangePop();
+        open_stage = i < CW_FUSED_STAGES ? i : -1;
+        if (open_stage >= 0) nvtxRangePushA(stage_names[i]);
+    };
+    struct StageCloser { int &s; ~StageCloser() { if (s >= 0) nvtxRangePop(); } } closer{open_stage};
     mark(0);
     const int D = fi->ix.D;
     const long long ldq = w->ldq;

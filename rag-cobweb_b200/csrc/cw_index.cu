@@ -2,6 +2,7 @@
 // src/cobweb/CobwebWrapper.py:186-203) in the operand form of the scoring kernel.
 // Strict arithmetic (-fmad=false): sumlog must equal the CPU oracle's bit for bit.
 #include "cw_common.cuh"
+#include "cw_nvtx.h"
 
 namespace cw {
 
@@ -105,6 +106,7 @@ void cw_set_error(const char *fmt, ...);
 int cw_check_cuda(cudaError_t e, const char *what);
 
 extern "C" int cw_index_build(const cw_store *s, const int32_t *order, int32_t nn, const cw_index *ix, void *stream) {
+    CwRange range("cw_index_build");
     if (!s || !order || !ix || nn < 1 || ix->D != s->D || ix->nn != nn || !ix->R || !ix->MB || !ix->sumlog ||
         ix->n_ntiles != (nn + CW_TILE_N - 1) / CW_TILE_N || ix->n_ktiles != (s->D + CW_TILE_K - 1) / CW_TILE_K) {
         cw_set_error("cw_index_build: bad argument / inconsistent index header");
