@@ -240,10 +240,25 @@ def _run_engine(args, wl):
     peaks, peak_src = measured_peaks()
 
     # ---------------------------------------------------------------- setup (untimed)
-    if rank == 0:
+    if rank == 0 and args.snapshot and os.path.exists(args.snapshot):
+        # a tree built by an earlier run of this bench on this box (the 1M-document build takes minutes): same tree
+        from rag_cobweb_b200 import CobwebWrapper
+        t0 = time.time()
+        w = CobwebWrapper.load_snapshot(args.snapshot)
+        x = synth.corpus(docs, dim, kind, seed=0)
+        meta = json.load(open(args.snapshot + ".json"))
+        assert (meta["docs"], meta["dim"], meta["kind"]) == (docs, dim, kind) and len(w.sentences) == docs, "snapshot of another workload"
+        build_s, counters = meta["build_s"], meta["counters"]
+        log(f"[bench] snapshot {args.snapshot} loaded in {time.time() - t0:.1f}s (built in {build_s:.1f}s)")
+    elif rank == 0:
         w, x, build_s = build_tree(docs, dim, kind)
         counters = w.tree.store.counters()
         log(f"[bench] ifit {docs}x{dim}: {build_s:.1f}s = {docs / build_s:.0f} inserts/s")
+        if args.snapshot:
+            t0 = time.time()
+            w.save_snapshot(args.snapshot)
+            json.dump({"docs": docs, "dim": dim, "kind": kind, "build_s": build_s, "counters": counters}, open(args.snapshot + ".json", "w"))
+            log(f"[bench] snapshot written to {args.snapshot} in {time.time() - t0:.1f}s")
     else:
         from rag_cobweb_b200 import CobwebWrapper
         x = synth.corpus(docs, dim, kind, seed=0)
@@ -579,7 +594,9 @@ def _run_engine(args, wl):
         "recall_at_k": recall,
         "parity": parity,
         "stages_ms": stages,
-        "fused_stats": {**fstats, "candidates_per_query": fstats["candidates"] / max(fstats["queries"], 1)} if fused else None,
+        "fused_stats": {**fstats, "candidates_per_query": fstats["candidates"] / max(fstats["queries"], 1),
+                        "refined_per_query": fstats["refined"] / max(fstats["queries"], 1),
+                        "rescored_per_query": fstats["rescored"] / max(fstats["queries"], 1)} if fused else None,
         "fp32_path": fp32,
         "brute_force_ip": brute,
         "single_query": single,
@@ -610,6 +627,8 @@ def main():
     ap.add_argument("--docs", type=int)
     ap.add_argument("--queries", type=int)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--snapshot", help="binary snapshot of the built tree: written after the build if missing, loaded instead of "
+                                       "building if present (several runs of the 1M-document workload on one box)")
     ap.add_argument("--mode", default="fused", choices=["fused", "fp32"],
                     help="fused (default): tcgen05 fp16 pipeline (3-product internal rows, 1-product leaf filter with a derived "
                          "bound) + exact FP32 refine / re-score; fp32: everything on the FP32 pipe.  The results are identical")

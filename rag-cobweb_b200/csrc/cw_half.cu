@@ -971,6 +971,7 @@ h_finish_kernel(const FinArgs a) {
         __syncthreads();
         const int m = misc[1];
         if (m > MS || misc[2] > MAXS) fail = fail ? fail : 3;
+        if (tid == 0) { atomicAdd(a.stats + 10, nsel); atomicAdd(a.stats + 11, m); }
         if (fail) {  // flagged: the exact small-batch path answers this query
             if (tid == 0) {
                 const int at = atomicAdd(a.flag, 1);
@@ -1264,12 +1265,16 @@ static int fused_chunk(const cw_fused_index *fi, const cw_fused_work *w, const f
             return rc;
     }
     h_unresolved_kernel<<<1, 1, 0, st>>>(w->flag, CW_FUSED_FB_ROUNDS * CW_SMALL_Q, w->stats);
-    if (w->audit_every > 0) {
+    // The exact answer of even one query streams all node operands once, so the audit runs in one call out of
+    // CW_FUSED_AUDIT_STRIDE with that many times the queries: the same audited fraction at a quarter of the cost.
+    if (w->audit_every > 0 && w->audit_phase % CW_FUSED_AUDIT_STRIDE == 0) {
         // the audited queries' exact answers land in sm_sid / sm_val; their list sits behind the flagged queries
-        long long n_a = (nq + w->audit_every - 1) / w->audit_every;
+        long long every = w->audit_every / CW_FUSED_AUDIT_STRIDE;
+        if (every < 1) every = 1;
+        long long n_a = (nq + every - 1) / every;
         if (n_a > CW_SMALL_Q) n_a = CW_SMALL_Q;
         int *which = w->flag + 4 + w->cap_q;
-        h_audit_pick_kernel<<<1, CW_SMALL_Q, 0, st>>>(which, (int)n_a, w->audit_every, w->audit_phase % w->audit_every, nq);
+        h_audit_pick_kernel<<<1, CW_SMALL_Q, 0, st>>>(which, (int)n_a, (int)every, (int)((w->audit_phase / CW_FUSED_AUDIT_STRIDE) % every), nq);
         if ((rc = cw_small_predict_impl(&fi->ix, Q, n_a, which, nullptr, 0, 0, k, w->sm_Q, w->sm_scores, w->sm_scratch, w->sm_sid,
                                         w->sm_val, w->sm_n, out_sid, out_val, st)))
             return rc;

@@ -27,7 +27,7 @@ from .tree import CobwebNode, CobwebTorchTree
 class DenseIndex:
     """Device-resident prediction index (build_prediction_index, CobwebWrapper.py:91-208)."""
 
-    SCORE_BUDGET_BYTES = 16 << 30  # node-score scratch per query chunk
+    SCORE_BUDGET_BYTES = 24 << 30  # node-score scratch per query chunk (180 GB of HBM: one chunk for 16k queries x 313k internal rows)
     # How the top-k of a query batch is computed (ids and scores are the same bit for bit in both modes):
     #   "fp32"   every (query, node) score on the FP32 pipe, (x*r + mb)^2 per triple (cw_dense.cu), path product and
     #            top-k over the [nodes, queries] score matrix: the form that DEFINES the result;
@@ -107,7 +107,7 @@ class DenseIndex:
         self.audit_every = self.AUDIT_EVERY
         self._audit_phase = 0
         self.stats = {"queries": 0, "flagged": 0, "unresolved": 0, "cand_overflow": 0, "line_fail": 0, "list_overflow": 0,
-                      "candidates": 0, "audited": 0, "audit_mismatch": 0}
+                      "candidates": 0, "audited": 0, "audit_mismatch": 0, "refined": 0, "rescored": 0}
 
     # ------------------------------------------------------------------ modes
     def set_mode(self, mode):
@@ -307,7 +307,7 @@ class DenseIndex:
         s["flagged"] += int(st[0]); s["unresolved"] += int(st[1]); s["cand_overflow"] += int(st[2])
         s["line_fail"] += int(st[3]); s["list_overflow"] += int(st[4]); s["queries"] += int(st[5])
         s["candidates"] += int(np.asarray(st[6:8], np.int32).view(np.uint64)[0])
-        s["audited"] += int(st[8]); s["audit_mismatch"] += int(st[9])
+        s["audited"] += int(st[8]); s["audit_mismatch"] += int(st[9]); s["refined"] += int(st[10]); s["rescored"] += int(st[11])
         if int(st[9]):
             self.eps_scale *= 4.0
             import warnings

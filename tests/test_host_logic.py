@@ -332,7 +332,7 @@ def test_fused_mode_host_policy():
     ix.nn, ix.mode = 20000, "fp32"
     assert not ix.fused_ready(10)
     ix.stats = {"queries": 0, "flagged": 0, "unresolved": 0, "cand_overflow": 0, "line_fail": 0, "list_overflow": 0,
-                "candidates": 0, "audited": 0, "audit_mismatch": 0}
+                "candidates": 0, "audited": 0, "audit_mismatch": 0, "refined": 0, "rescored": 0}
     ix.eps_scale = DenseIndex.EPS_SCALE
     st = np.zeros(_lib.FUSED_STATS, np.int32)
     st[0], st[2], st[3], st[5], st[8] = 3, 1, 2, 10000, 5
