@@ -786,15 +786,15 @@ struct FinArgs {
 __host__ __device__ inline size_t fin_smem_bytes(int D, int ML, int cap) {
     const size_t E = (size_t)MS * ML;
     return (size_t)ML * 8 + (size_t)FN_WARPS * FN_R * 33 * 8 + (size_t)((D + 3) & ~3) * 4 + (size_t)cap * 14 + (size_t)KC1 * 36 +
-           E * 12 + E * 4 + (size_t)MS * 12 + (size_t)MAXS * 8 + 64 + 16;
+           E * 12 + E * 4 + (size_t)MS * 12 + (size_t)MAXS * 8 + 64 + 16 + 16 + 8 + (size_t)FN_WARPS * FN_R * 8 + 8;
 }
 
 __global__ void __launch_bounds__(FN_THREADS)
 h_finish_kernel(const FinArgs a) {
     extern __shared__ __align__(16) unsigned char fn_smem[];
     const int D = a.ix.D, ML = a.ix.max_len, cap = a.cap, EMAX = MS * ML;
-    double *lw = reinterpret_cast<double *>(fn_smem);                     // [ML]
-    float2 *stage = reinterpret_cast<float2 *>(lw + ML);                  // [FN_WARPS][FN_R][33]
+    double *lw = reinterpret_cast<double *>(fn_smem);                     // [ML] (rounded to 16 bytes)
+    float2 *stage = reinterpret_cast<float2 *>(lw + ((ML + 1) & ~1));     // [FN_WARPS][FN_R][33]
     float *xq = reinterpret_cast<float *>(stage + FN_WARPS * FN_R * 33);  // [D]
     float *cv = xq + ((D + 3) & ~3);                                      // [cap] candidate a1
     int *cr = reinterpret_cast<int *>(cv + cap);                          // [cap] candidate leaf row
@@ -822,58 +822,93 @@ h_finish_kernel(const FinArgs a) {
     float *lval = reinterpret_cast<float *>(lsid + MAXS);                 // [MAXS]
     int *misc = reinterpret_cast<int *>(lval + MAXS);                     // [16] counters and broadcast values
     unsigned short *byrank = reinterpret_cast<unsigned short *>(misc + 16);  // [cap] candidate with a1 rank r
+    const float2 **rowp_s = reinterpret_cast<const float2 **>(byrank + ((cap + 3) & ~3));  // [FN_WARPS][FN_R] row pointers
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float NEG_INF = -__int_as_float(0x7f800000);
     for (int i = tid; i < ML; i += FN_THREADS) lw[i] = a.ix.level_w[i];
 
-    // exact node scores of the rows list[0..U) with the FP32 path's arithmetic: rows dealt evenly to the warps,
-    // lane = row; per 32 attributes a warp reads its rows with coalesced 256-byte loads (all in flight at once and one
-    // segment ahead of the arithmetic), transposes them through shared memory, every lane runs its row's chain.
-    // R = rows a warp handles at a time (8 or FN_R = 16: the loops over rows are unrolled for it).
-    auto exact_rows_r = [&](auto rtag, const int *list, int lo, int n_rows, float *outs) {
+    // exact node scores of the rows list[0..U) with the FP32 path's arithmetic.  The rows are cut into rounds of at
+    // most FN_R; a warp takes a round: lane = row for the arithmetic (every lane runs its row's FMA chain in order),
+    // lane = attribute for the loads (per 32 attributes one coalesced 256-byte load per row, one or two segments ahead
+    // of the arithmetic), transposed through shared memory.  Rounds are packed densely -- the chain phase costs the same
+    // whether a warp holds 1 row or 16, so 13 rows are ONE warp's round, not four.
+    auto exact_round = [&](auto rtag, const int *list, int lo, int cnt, float *outs) {
         constexpr int R = decltype(rtag)::value;
+        constexpr int DEPTH = R <= 8 ? 2 : 1;  // segments in flight ahead of the arithmetic (registers: 2 R per segment)
         float2 *stw = stage + warp * FN_R * 33;
-        for (int base0 = lo; base0 < lo + n_rows; base0 += R) {
-            const int u = base0 + lane;
-            const int b = (lane < R && u < lo + n_rows) ? list[u] : -1;
-            float acc = 0.0f;
-            float2 o[R];
-            auto fetch = [&](int d0) {
+        const float2 **rowp = rowp_s + warp * FN_R;
+        const int b = lane < cnt ? list[lo + lane] : -1;
+        if (lane < R) rowp[lane] = a.RM + (size_t)(b < 0 ? 0 : b) * D;
+        __syncwarp();
+        float acc = 0.0f;
+        float2 o[DEPTH][R];
+        auto fetch = [&](int d0, float2 (&dst)[R]) {
+            const bool dok = d0 + lane < D;
 #pragma unroll
-                for (int r = 0; r < R; r++) {
-                    const int rb = __shfl_sync(0xffffffffu, b, r);
-                    o[r] = make_float2(0.0f, 0.0f);
-                    if (rb >= 0 && d0 + lane < D) o[r] = a.RM[(size_t)rb * D + d0 + lane];
-                }
-            };
-            fetch(0);
-            for (int d0 = 0; d0 < D; d0 += 32) {
+            for (int r = 0; r < R; r++) {
+                dst[r] = make_float2(0.0f, 0.0f);
+                if (r < cnt && dok) dst[r] = rowp[r][d0 + lane];  // r < cnt is warp-uniform
+            }
+        };
 #pragma unroll
-                for (int r = 0; r < R; r++) stw[r * 33 + lane] = o[r];
+        for (int p = 0; p < DEPTH; p++) fetch(32 * p, o[p]);
+        for (int d0 = 0; d0 < D; d0 += 32 * DEPTH) {
+#pragma unroll
+            for (int p = 0; p < DEPTH; p++) {
+                const int dd = d0 + 32 * p;
+                if (dd >= D) break;  // warp-uniform
+#pragma unroll
+                for (int r = 0; r < R; r++) stw[r * 33 + lane] = o[p][r];
                 __syncwarp();
-                if (d0 + 32 < D) fetch(d0 + 32);
-                if (lane < R) {
-                    const int nd = min(32, D - d0);
-                    for (int j = 0; j < nd; j++) {
-                        const float2 v = stw[lane * 33 + j];
-                        const float t = __fmaf_rn(xq[d0 + j], v.x, v.y);
-                        acc = __fmaf_rn(t, t, acc);
+                if (dd + 32 * DEPTH < D) fetch(dd + 32 * DEPTH, o[p]);
+                if (lane < cnt) {
+                    if (dd + 32 <= D) {
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; j4++) {
+                            const float4 xv = *reinterpret_cast<const float4 *>(xq + dd + 4 * j4);
+                            const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                            for (int e = 0; e < 4; e++) {
+                                const float2 v = stw[lane * 33 + 4 * j4 + e];
+                                const float t = __fmaf_rn(xs[e], v.x, v.y);
+                                acc = __fmaf_rn(t, t, acc);
+                            }
+                        }
+                    } else {
+                        for (int j = 0; j < D - dd; j++) {
+                            const float2 v = stw[lane * 33 + j];
+                            const float t = __fmaf_rn(xq[dd + j], v.x, v.y);
+                            acc = __fmaf_rn(t, t, acc);
+                        }
                     }
                 }
                 __syncwarp();
             }
-            if (b >= 0) outs[u] = -0.5f * (a.ix.sumlog[b] + acc);
         }
+        if (b >= 0) outs[lo + lane] = -0.5f * (a.ix.sumlog[b] + acc);
     };
     auto exact_rows = [&](const int *list, int U, float *outs) {
-        const int per = (U + FN_WARPS - 1) / FN_WARPS;
-        const int lo = warp * per, cnt = max(0, min(per, U - lo));
-        if (cnt == 0) return;  // warp-uniform
-        if (per <= 8) exact_rows_r(std::integral_constant<int, 8>{}, list, lo, cnt, outs);
-        else exact_rows_r(std::integral_constant<int, FN_R>{}, list, lo, cnt, outs);  // rounds of FN_R rows
+        if (U <= 0) return;
+        const int n_rounds = (U + FN_R - 1) / FN_R, rpr = (U + n_rounds - 1) / n_rounds;  // rows per round <= FN_R
+        for (int rd = warp; rd < n_rounds; rd += FN_WARPS) {
+            const int lo = rd * rpr, cnt = min(rpr, U - lo);
+            if (cnt <= 0) continue;
+            if (rpr <= 8) exact_round(std::integral_constant<int, 8>{}, list, lo, cnt, outs);
+            else exact_round(std::integral_constant<int, FN_R>{}, list, lo, cnt, outs);
+        }
+    };
+    // the rows a phase is about to score exactly are random 8 D-byte rows of a 0.8 GB array: ask for them in L2 as
+    // soon as the list is known, so that the segment loads of exact_rows find them there
+    auto prefetch_rows = [&](const int *list, int U) {
+        const int lines = (D * 8 + 127) / 128;
+        for (int i = tid; i < U * lines; i += FN_THREADS) {
+            const int b = list[i / lines];
+            if (b >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(a.RM + (size_t)b * D) + (size_t)(i % lines) * 128));
+        }
     };
 
+    int n_refined = 0, n_rescored = 0;  // counters of this CTA's queries, added to the stats once at the end
     for (long long q = blockIdx.x; q < a.nq; q += gridDim.x) {
         __syncthreads();
         for (int d = tid; d < D; d += FN_THREADS) xq[d] = a.Q[q * D + d];
@@ -932,6 +967,7 @@ h_finish_kernel(const FinArgs a) {
         }
         __syncthreads();
         const int nsel = misc[7];
+        prefetch_rows(sb, nsel);
         int fail = n_all > cap ? 1 : 0;  // candidate-buffer overflow
         const float U = fmaxf(a.tau[q], key_float(misc[5]));
         // ---- exact leaf terms of the selected candidates, a3 = (C[parent] + w s) / len
@@ -971,7 +1007,8 @@ h_finish_kernel(const FinArgs a) {
         __syncthreads();
         const int m = misc[1];
         if (m > MS || misc[2] > MAXS) fail = fail ? fail : 3;
-        if (tid == 0) { atomicAdd(a.stats + 10, nsel); atomicAdd(a.stats + 11, m); }
+        n_refined += nsel;
+        n_rescored += m;
         if (fail) {  // flagged: the exact small-batch path answers this query
             if (tid == 0) {
                 const int at = atomicAdd(a.flag, 1);
@@ -1008,6 +1045,7 @@ h_finish_kernel(const FinArgs a) {
             const int c = e / ML, j = e - c * ML, f = firstc[e];
             if (f != c) slot[e] = slot[f * ML + j];
         }
+        prefetch_rows(ulist, misc[0]);
         exact_rows(ulist, misc[0], uscore);
         __syncthreads();
         // ---- exact leaf scores: sequential FMA along the path, root first, the leaf last (cw_dense_paths_topk's order)
@@ -1042,6 +1080,7 @@ h_finish_kernel(const FinArgs a) {
             a.out_val[q * a.k + r] = NEG_INF;
         }
     }
+    if (tid == 0 && (n_refined | n_rescored)) { atomicAdd(a.stats + 10, n_refined); atomicAdd(a.stats + 11, n_rescored); }
 }
 
 __global__ void h_stats_kernel(const int *__restrict__ cnt, long long nq, int *stats) {
@@ -1294,7 +1333,7 @@ static bool fused_args_ok(const cw_fused_index *fi, const cw_fused_work *w, int 
         return false;
     if (fi->n_sample_tiles < 0 || fi->n_sample_tiles > fi->leaves.n_ntiles) return false;
     if (w->cap_q < TQ || (w->cap_q % TQ) || w->ldq != w->cap_q || !w->A_leaf || (fi->n_int && (!w->A_int || !w->S)) || !w->qv ||
-        !w->slots || !w->tau || w->cap < 1 || w->cap > 2048 || !w->cnt || !w->cand_val || !w->cand_row || !w->flag || !w->sm_Q ||
+        !w->slots || !w->tau || w->cap < 4 || w->cap > 2048 || (w->cap & 3) || !w->cnt || !w->cand_val || !w->cand_row || !w->flag || !w->sm_Q ||
         !w->sm_scores || !w->sm_scratch || !w->sm_sid || !w->sm_val || !w->sm_n || !w->stats)
         return false;
     return true;
