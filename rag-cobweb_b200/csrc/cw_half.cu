@@ -29,6 +29,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <type_traits>
 
@@ -46,17 +47,10 @@ constexpr int TN = CW_H_TILE;   // index rows per tile (UMMA N)
 constexpr int ROWB = 64;        // bytes per operand row of a slab (32 fp16)
 constexpr int IMG = CW_H_IMG_BYTES;
 constexpr int SIDE = CW_H_STAGE_BYTES;  // A resp. B part of a stage: two images
-constexpr int STAGE_BYTES = 2 * SIDE;   // 64 KB
-constexpr int NSTAGE = 3;
-constexpr int EPI_WARPS = 16;   // four per TMEM lane quarter
-constexpr int THREADS = 64 + 32 * EPI_WARPS;  // producer warp, MMA warp, epilogue warps
-constexpr int EPI_THREADS = THREADS - 64;
 constexpr int BW = 16;          // accumulator columns (index rows) an epilogue thread handles at a time
 constexpr int REC_FLOATS = 8;
-constexpr int REC_BYTES = 2 * TN * REC_FLOATS * 4 + 2 * TN * 8 + 128;  // two tiles of leaf records, parent-row byte offsets, run masks
-constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */ + REC_BYTES;
 static_assert(IMG == TN * ROWB && SIDE == 2 * IMG, "stage geometry");
-static_assert(EPI_THREADS >= TN && EPI_WARPS % 4 == 0 && BW * 2 == 32, "epilogue geometry");
+static_assert(BW * 2 == 32, "epilogue geometry");
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -199,33 +193,58 @@ struct HEpi {
     int *cand_row;        // FILTER: [nq, cap]
 };
 
-template <int NPROD, int MODE>
-__global__ void __launch_bounds__(THREADS, 1)
+// Two tile shapes.  FULL: 256 queries x 256 rows per CTA, one CTA per SM, all 512 TMEM columns: the least operand traffic
+// per MMA (the three-product kernel of the internal rows is tensor-bound and wants exactly that).  HALF: 128 queries x
+// 256 rows, TWO CTAs per SM with 256 TMEM columns each: the one-product kernels alternate between an MMA phase that waits
+// on operands and an epilogue that cannot overlap it inside one CTA (the tile owns its accumulator until it is drained) --
+// with two CTAs per SM one computes while the other drains, for 1.5x the operand traffic.
+template <bool HALF>
+struct KCfg {
+    static constexpr int TQK = HALF ? 128 : 256;         // queries per CTA tile
+    static constexpr int NQH = TQK / TM;                 // accumulators (128-query halves)
+    static constexpr int A_IMG = HALF ? IMG / 2 : IMG;   // bytes of one query-operand image the CTA holds
+    static constexpr int A_SIDE = 2 * A_IMG;
+    static constexpr int STAGE = A_SIDE + SIDE;
+    static constexpr int NST = HALF ? 2 : 3;
+    static constexpr int EPIW = HALF ? 8 : 16;           // epilogue warps
+    static constexpr int THR = 64 + 32 * EPIW;
+    static constexpr int EPI_THR = 32 * EPIW;
+    static constexpr int RBUFS = HALF ? 1 : 2;           // leaf-record buffers
+    static constexpr int TMEM_COLS = HALF ? 256 : 512;
+    static constexpr int REC = RBUFS * (TN * REC_FLOATS * 4 + TN * 8 + 64);
+    static constexpr int SMEM = NST * STAGE + 1024 /* alignment slack */ + 256 /* barriers */ + REC;
+    static constexpr int CTAS = HALF ? 2 : 1;
+};
+static_assert(KCfg<true>::SMEM * 2 + 2048 <= 227 * 1024 + 1024, "two half-tile CTAs per SM");
+
+template <int NPROD, int MODE, bool HALF>
+__global__ void __launch_bounds__(KCfg<HALF>::THR, KCfg<HALF>::CTAS)
 h_score_kernel(const unsigned char *__restrict__ A, const unsigned char *__restrict__ B, const HEpi epi, int n_qtiles,
                int nt_begin, int n_ntiles, int n_stages, int pq) {
+    using K = KCfg<HALF>;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // swizzle atoms need their natural alignment
-    const uint32_t bars = base + NSTAGE * STAGE_BYTES;
-    // barrier words: full[NSTAGE], empty[NSTAGE], acc_full, acc_empty, then the TMEM base address
-    const uint32_t full0 = bars, empty0 = bars + 8 * NSTAGE, accf = bars + 16 * NSTAGE, acce = accf + 8;
+    const uint32_t bars = base + K::NST * K::STAGE;
+    // barrier words: full[NST], empty[NST], acc_full, acc_empty, then the TMEM base address
+    const uint32_t full0 = bars, empty0 = bars + 8 * K::NST, accf = bars + 16 * K::NST, acce = accf + 8;
     const uint32_t tmem_slot = acce + 8;
     uint32_t *tmem_slot_ptr = reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
-    float4 *recs_s = reinterpret_cast<float4 *>(smem_raw + (bars + 256 - smem_u32(smem_raw)));  // [2][TN][2]
-    long long *coff_s = reinterpret_cast<long long *>(recs_s + 2 * TN * 2);                       // [2][TN]
-    unsigned *heads_s = reinterpret_cast<unsigned *>(coff_s + 2 * TN);                            // [2][8] run heads, [2][8] heads to load
+    float4 *recs_s = reinterpret_cast<float4 *>(smem_raw + (bars + 256 - smem_u32(smem_raw)));  // [RBUFS][TN][2]
+    long long *coff_s = reinterpret_cast<long long *>(recs_s + K::RBUFS * TN * 2);                // [RBUFS][TN]
+    unsigned *heads_s = reinterpret_cast<unsigned *>(coff_s + K::RBUFS * TN);                     // [RBUFS][8 run heads, 8 heads to load]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NSTAGE; s++) {
+        for (int s = 0; s < K::NST; s++) {
             mbar_init(full0 + 8 * s, 1);
             mbar_init(empty0 + 8 * s, 1);
         }
         mbar_init(accf, 1);
-        mbar_init(acce, EPI_THREADS / 32);  // one arrival per epilogue warp
+        mbar_init(acce, K::EPIW);  // one arrival per epilogue warp
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {  // TMEM: all 512 columns (two 128 x 256 fp32 accumulators); this warp also frees them
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(512) : "memory");
+    if (warp == 1) {  // TMEM: one 128 x 256 fp32 accumulator per 128 queries of the tile; this warp also frees them
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(K::TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -242,15 +261,21 @@ h_score_kernel(const unsigned char *__restrict__ A, const unsigned char *__restr
             for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
                 int nt, qt;
                 tile_coords(t, n_qtiles, n_ntiles, pq, nt, qt);
-                const unsigned char *asrc = A + (size_t)qt * n_stages * SIDE;
+                // the query operands are stored per 256-query tile; a half tile takes rows 128 (qt & 1) .. of both images
+                const unsigned char *asrc = A + (size_t)(HALF ? qt >> 1 : qt) * n_stages * SIDE + (HALF ? (qt & 1) * (IMG / 2) : 0);
                 const unsigned char *bsrc = B + (size_t)(nt_begin + nt) * n_stages * SIDE;
                 for (int s = 0; s < n_stages; s++) {
                     mbar_wait(empty0 + 8 * stage, phase ^ 1);
-                    const uint32_t sb = base + stage * STAGE_BYTES;
-                    mbar_arrive_expect_tx(full0 + 8 * stage, STAGE_BYTES);
-                    bulk_g2s(sb, asrc + (size_t)s * SIDE, SIDE, full0 + 8 * stage);
-                    bulk_g2s(sb + SIDE, bsrc + (size_t)s * SIDE, SIDE, full0 + 8 * stage);
-                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                    const uint32_t sb = base + stage * K::STAGE;
+                    mbar_arrive_expect_tx(full0 + 8 * stage, K::STAGE);
+                    if (HALF) {
+                        bulk_g2s(sb, asrc + (size_t)s * SIDE, IMG / 2, full0 + 8 * stage);
+                        bulk_g2s(sb + IMG / 2, asrc + (size_t)s * SIDE + IMG, IMG / 2, full0 + 8 * stage);
+                    } else {
+                        bulk_g2s(sb, asrc + (size_t)s * SIDE, SIDE, full0 + 8 * stage);
+                    }
+                    bulk_g2s(sb + K::A_SIDE, bsrc + (size_t)s * SIDE, SIDE, full0 + 8 * stage);
+                    if (++stage == K::NST) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -267,15 +292,15 @@ h_score_kernel(const unsigned char *__restrict__ A, const unsigned char *__restr
                 for (int s = 0; s < n_stages; s++) {
                     mbar_wait(full0 + 8 * stage, phase);
                     tc_fence_after();
-                    const uint32_t sb = base + stage * STAGE_BYTES;
+                    const uint32_t sb = base + stage * K::STAGE;
                     if (NPROD == 3) {
                         // images: A hi, A lo | B hi, B lo of one slab
-                        const uint64_t b_hi = make_smem_desc(sb + SIDE), b_lo = make_smem_desc(sb + SIDE + IMG);
+                        const uint64_t b_hi = make_smem_desc(sb + K::A_SIDE), b_lo = make_smem_desc(sb + K::A_SIDE + IMG);
 #pragma unroll
-                        for (int qh = 0; qh < 2; qh++) {  // the two 128-query halves of the tile, one accumulator each
+                        for (int qh = 0; qh < K::NQH; qh++) {  // the 128-query halves of the tile, one accumulator each
                             const uint32_t d = tmem_base + (uint32_t)(qh * TN);
                             const uint64_t a_hi = make_smem_desc(sb + qh * (TM * ROWB));
-                            const uint64_t a_lo = make_smem_desc(sb + IMG + qh * (TM * ROWB));
+                            const uint64_t a_lo = make_smem_desc(sb + K::A_IMG + qh * (TM * ROWB));
 #pragma unroll
                             for (int k = 0; k < ROWB / 32; k++) {  // 16 fp16 = 32 bytes per MMA; +2 in 16-byte address units
                                 const uint64_t ko = (uint64_t)(2 * k);
@@ -288,11 +313,11 @@ h_score_kernel(const unsigned char *__restrict__ A, const unsigned char *__restr
                         // images: A slab 2s, A slab 2s+1 | B slab 2s, B slab 2s+1
 #pragma unroll
                         for (int g = 0; g < 2; g++) {
-                            const uint64_t b_g = make_smem_desc(sb + SIDE + g * IMG);
+                            const uint64_t b_g = make_smem_desc(sb + K::A_SIDE + g * IMG);
 #pragma unroll
-                            for (int qh = 0; qh < 2; qh++) {
+                            for (int qh = 0; qh < K::NQH; qh++) {
                                 const uint32_t d = tmem_base + (uint32_t)(qh * TN);
-                                const uint64_t a_g = make_smem_desc(sb + g * IMG + qh * (TM * ROWB));
+                                const uint64_t a_g = make_smem_desc(sb + g * K::A_IMG + qh * (TM * ROWB));
 #pragma unroll
                                 for (int k = 0; k < ROWB / 32; k++) {
                                     const uint64_t ko = (uint64_t)(2 * k);
@@ -303,18 +328,19 @@ h_score_kernel(const unsigned char *__restrict__ A, const unsigned char *__restr
                     }
                     tc_commit(empty0 + 8 * stage);  // stage free once these MMAs have read it
                     if (s == n_stages - 1) tc_commit(accf);
-                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                    if (++stage == K::NST) { stage = 0; phase ^= 1; }
                 }
                 aphase ^= 1;
             }
         }
         __syncwarp();
     } else {
-        // ===== epilogue: sixteen warps; warp w reads TMEM lanes 32*(w%4) .. +31 (lane = query of the 128-query half),
-        // the four warps of a lane quarter take every fourth 16-column block.  The work per (query, row) is a dozen
+        // ===== epilogue: sixteen warps (eight for a half tile); warp w reads TMEM lanes 32*(w%4) .. +31 (lane = query of
+        // the 128-query half), the warps of a lane quarter take 16-column blocks in turn.  The work per (query, row) is a dozen
         // dependent instructions on two shared-memory reads: latency-bound, so the more warps the better; 16 columns at
         // a time keep a thread under the 112 registers that 576 threads per SM allow.
-        const int quarter = warp & 3, sub = (warp - 2) >> 2;  // sub 0..3
+        const int quarter = warp & 3, sub = (warp - 2) >> 2;  // sub 0 .. EPIW/4 - 1
+        constexpr int WPQ = K::EPIW / 4;                       // warps per lane quarter
         uint32_t aphase = 0;
         int rbuf = 0;
         const long long ldq = epi.ldq;
@@ -322,20 +348,20 @@ h_score_kernel(const unsigned char *__restrict__ A, const unsigned char *__restr
             int nt, qt;
             tile_coords(t, n_qtiles, n_ntiles, pq, nt, qt);
             const long long n0 = (long long)(nt_begin + nt) * TN;
-            const long long qbase = (long long)qt * TQ + quarter * 32 + lane;
+            const long long qbase = (long long)qt * K::TQK + quarter * 32 + lane;
             if (MODE == EPI_NODE) {
                 const float2 *rc2 = reinterpret_cast<const float2 *>(epi.rc);
                 mbar_wait(accf, aphase);
                 tc_fence_after();
 #pragma unroll 1
-                for (int qh = 0; qh < 2; qh++) {
-                    const long long q0 = (long long)qt * TQ + qh * TM;
+                for (int qh = 0; qh < K::NQH; qh++) {
+                    const long long q0 = (long long)qt * K::TQK + qh * TM;
                     if (q0 >= ldq) break;  // a half-tile of pure padding past the score matrix
                     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(qh * TN);
                     const long long q = qbase + qh * TM;
                     const float sa = epi.qv[q].w;
 #pragma unroll 1
-                    for (int cb = sub; cb < TN / BW; cb += EPI_WARPS / 4) {
+                    for (int cb = sub; cb < TN / BW; cb += WPQ) {
                         uint32_t v[BW];
                         CWH_TMEM_LD16(taddr + (uint32_t)(cb * BW), v);
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -350,6 +376,8 @@ h_score_kernel(const unsigned char *__restrict__ A, const unsigned char *__restr
             } else {
                 // the tile's leaf records go to shared memory while the MMAs of the tile are still running; two
                 // buffers, so that one named barrier per tile also protects the buffer of the tile before
+                if (K::RBUFS == 1 && t != (long long)blockIdx.x)
+                    asm volatile("bar.sync 1, %0;" ::"n"(K::EPI_THR) : "memory");  // one buffer: everyone is done with the previous tile's records
                 const float4 *recs = recs_s + rbuf * (TN * 2);
                 const long long *coff = coff_s + rbuf * TN;
                 const unsigned *heads = heads_s + rbuf * 16;
@@ -369,17 +397,20 @@ h_score_kernel(const unsigned char *__restrict__ A, const unsigned char *__restr
                         const unsigned hm = __ballot_sync(0xffffffffu, head), lm = __ballot_sync(0xffffffffu, head && par >= 0);
                         if (lane == 0) { heads_s[rbuf * 16 + (e >> 5)] = hm; heads_s[rbuf * 16 + 8 + (e >> 5)] = lm; }
                     }
-                    asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
-                    rbuf ^= 1;
+                    asm volatile("bar.sync 1, %0;" ::"n"(K::EPI_THR) : "memory");
+                    if (K::RBUFS == 2) rbuf ^= 1;
                 }
                 // This warp's eight batches of 16 rows: b -> (query half b / 4, column block sub + 4 (b % 4)).  The
                 // ancestor sums C[parent][q] of a batch do not depend on the accumulator, so they are fetched one batch
                 // ahead -- the first batch while the MMAs of the tile are still running -- and only for the run heads
                 // (predicated loads, all in flight together); the other rows carry their predecessor's value along.
-                auto heads_of = [&](int b) { const int cb = sub + 4 * (b & 3); return (heads[cb >> 1] >> ((cb & 1) * BW)) & 0xffffu; };
+                // batch b of this warp -> (query half, 16-column block)
+                auto half_of = [&](int b) { return HALF ? 0 : b >> 2; };
+                auto block_of = [&](int b) { return HALF ? sub + WPQ * b : sub + WPQ * (b & 3); };
+                auto heads_of = [&](int b) { const int cb = block_of(b); return (heads[cb >> 1] >> ((cb & 1) * BW)) & 0xffffu; };
                 auto fetch_cp = [&](int b, float (&cp)[BW]) {
-                    const int qh = b >> 2, cb = sub + 4 * (b & 3);
-                    const bool qok = (long long)qt * TQ + qh * TM < ldq;
+                    const int qh = half_of(b), cb = block_of(b);
+                    const bool qok = (long long)qt * K::TQK + qh * TM < ldq;
                     const char *Cq = reinterpret_cast<const char *>(epi.C + qbase + qh * TM);
                     const unsigned lm = qok ? (heads[8 + (cb >> 1)] >> ((cb & 1) * BW)) & 0xffffu : 0u;
 #pragma unroll
@@ -416,8 +447,8 @@ h_score_kernel(const unsigned char *__restrict__ A, const unsigned char *__restr
                 tc_fence_after();
 #pragma unroll 1
                 for (int b = 0; b < 8; b++) {
-                    const int qh = b >> 2, cb = sub + 4 * (b & 3);
-                    if ((long long)qt * TQ + qh * TM >= ldq) break;  // a half-tile of pure padding past the score matrix
+                    const int qh = half_of(b), cb = block_of(b);
+                    if ((long long)qt * K::TQK + qh * TM >= ldq) break;  // a half-tile of pure padding past the score matrix
                     const long long q = qbase + qh * TM;
                     uint32_t v[BW];
                     CWH_TMEM_LD16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(qh * TN + cb * BW), v);
@@ -464,7 +495,7 @@ h_score_kernel(const unsigned char *__restrict__ A, const unsigned char *__restr
                             }
                         }
                     }
-                    if (MODE == EPI_TAU && (b & 3) == 3) {
+                    if (MODE == EPI_TAU && (HALF ? b == 7 : (b & 3) == 3)) {
                         // this query half is done: publish the slot maxima that beat what the slots already hold
                         if (live) {
                             int *sl = epi.slots + q * 32 + (sub & 1) * BW;
@@ -495,7 +526,7 @@ h_score_kernel(const unsigned char *__restrict__ A, const unsigned char *__restr
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(K::TMEM_COLS) : "memory");
     }
 }
 
@@ -1163,26 +1194,34 @@ extern "C" int cw_h_rows_isotropic(const cw_store *s, const int32_t *order, cons
     return out;
 }
 
-template <int NPROD, int MODE>
-static int h_launch(const cw_h_set *hs, const void *A, int64_t nq, int nt_begin, int nt_count, const HEpi &epi, cudaStream_t st) {
-    const int n_qtiles = (int)((nq + TQ - 1) / TQ);
-    auto kern = h_score_kernel<NPROD, MODE>;
-    int rc = cw_check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES), "cw_h: smem attribute");
+template <int NPROD, int MODE, bool HALF>
+static int h_launch_t(const cw_h_set *hs, const void *A, int64_t nq, int nt_begin, int nt_count, const HEpi &epi, cudaStream_t st) {
+    using K = KCfg<HALF>;
+    const int n_qtiles = (int)((nq + K::TQK - 1) / K::TQK);
+    auto kern = h_score_kernel<NPROD, MODE, HALF>;
+    int rc = cw_check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM), "cw_h: smem attribute");
     if (rc) return rc;
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long n_tiles = (long long)n_qtiles * nt_count;
     if (n_tiles == 0) return 0;
-    const int grid = (int)(n_tiles < sms ? n_tiles : sms);
+    const int grid = (int)(n_tiles < (long long)sms * K::CTAS ? n_tiles : sms * K::CTAS);
     // query-tile panels: the panel's query operands should sit in L2 (~40 MB of it) while the row operands stream
-    const long long a_tile = (long long)hs->n_stages * SIDE;
+    const long long a_tile = (long long)hs->n_stages * K::A_SIDE;
     int pq_max = (int)((40ll << 20) / a_tile);
     if (pq_max < 1) pq_max = 1;
     const int n_panels = (n_qtiles + pq_max - 1) / pq_max;
     const int pq = (n_qtiles + n_panels - 1) / n_panels;
-    kern<<<grid, THREADS, SMEM_BYTES, st>>>(reinterpret_cast<const unsigned char *>(A), reinterpret_cast<const unsigned char *>(hs->B),
-                                            epi, n_qtiles, nt_begin, nt_count, hs->n_stages, pq);
+    kern<<<grid, K::THR, K::SMEM, st>>>(reinterpret_cast<const unsigned char *>(A), reinterpret_cast<const unsigned char *>(hs->B),
+                                        epi, n_qtiles, nt_begin, nt_count, hs->n_stages, pq);
     return cw_check_cuda(cudaGetLastError(), "cw_h: score kernel");
+}
+// the one-product kernels take half tiles (two CTAs per SM) unless COBWEB_B200_FULL_TILE=1 asks for the full ones
+template <int NPROD, int MODE>
+static int h_launch(const cw_h_set *hs, const void *A, int64_t nq, int nt_begin, int nt_count, const HEpi &epi, cudaStream_t st) {
+    static const bool full_tile = getenv("COBWEB_B200_FULL_TILE") && atoi(getenv("COBWEB_B200_FULL_TILE")) != 0;
+    if (NPROD == 1 && !full_tile) return h_launch_t<NPROD, MODE, true>(hs, A, nq, nt_begin, nt_count, epi, st);
+    return h_launch_t<NPROD, MODE, false>(hs, A, nq, nt_begin, nt_count, epi, st);
 }
 
 int cw_small_predict_impl(const cw_index *ix, const float *Q, int64_t nq, const int32_t *which, const int32_t *n_dev,
