@@ -645,6 +645,14 @@ def test_fused_predict_sampled_threshold_and_overflow(n, d, kind, k, weights):
         assert ix.stats["candidates"] / ix.stats["queries"] < 0.2 * ix.hx["n_leaf"], ix.stats
     a, b, _ = ix.predict(qd[:40], k, small=False)  # one partial tile
     assert torch.equal(a, ids32[:40]) and torch.equal(b, v32[:40])
+    # several chunks per call (work buffers sized for 256 queries): device and host entry
+    budget, ix.SCORE_BUDGET_BYTES, ix._hws = ix.SCORE_BUDGET_BYTES, 1, None
+    assert ix.fused_chunk_queries() == 256
+    a, b, _ = ix.predict(qd, k)
+    hs, hv = ix.predict_host(q, k)
+    assert torch.equal(a, ids32) and torch.equal(b, v32) and np.array_equal(hs.numpy(), ids32.cpu().numpy())
+    assert np.array_equal(hv.numpy(), v32.cpu().numpy())
+    ix.SCORE_BUDGET_BYTES, ix._hws = budget, None
     # candidate-buffer overflow: with 8 slots per query nearly every query overflows, is flagged by the finish kernel and
     # answered by the exact path -- same result
     ix.FUSED_CAP, ix._hws, f0 = 8, None, ix.stats["cand_overflow"]

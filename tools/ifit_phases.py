@@ -1,0 +1,17 @@
+"""ifit phase timers (cw_ifit.cu MARK()) for a run: where a level-step spends its time.
+  python tools/ifit_phases.py [n] [d] [kind]"""
+import sys, time
+import numpy as np, torch
+sys.path.insert(0, '.')
+from rag_cobweb_b200 import CobwebTorchTree, synth
+n, d, kind = int(sys.argv[1]) if len(sys.argv) > 1 else 30000, int(sys.argv[2]) if len(sys.argv) > 2 else 768, sys.argv[3] if len(sys.argv) > 3 else "unit"
+x = torch.from_numpy(synth.corpus(n, d, kind, 0)).cuda()
+t = CobwebTorchTree((d,))
+torch.cuda.synchronize(); t0 = time.time()
+t.ifit_batch(x, tag_sentences=True)
+torch.cuda.synchronize(); dt = time.time() - t0
+c = t.store.counters()
+ph = t.store.ifit_phase_cycles()
+tot = sum(ph.values())
+print(f"{n}x{d} {kind}: {n / dt:.0f} inserts/s, {c['levels'] / n:.2f} levels/insert, {dt / c['levels'] * 1e6:.2f} us/level-step, rows/insert {c['rows'] / n:.1f}")
+print("phase share:", {k: round(v / max(tot, 1), 3) for k, v in ph.items()}, "cycles/level", {k: int(v / max(c['levels'], 1)) for k, v in ph.items()})

@@ -15,9 +15,9 @@ KEEP = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "l1tex__m_xbar2l1tex_read_bytes.sum", "l1tex__m_xbar2l1tex_read_bytes_mem_global_op_tma_ld.sum",
         "lts__throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
-        "sm__ops_path_tensor_op_utchmma_src_tf32_dst_fp32_sparsity_off.sum",
-        "sm__ops_path_tensor_op_utchmma_src_tf32_dst_fp32_sparsity_off.sum.per_second",
-        "sm__ops_path_tensor_op_utchmma_src_tf32_dst_fp32_sparsity_off.sum.peak_sustained_elapsed.per_second",
+        "sm__ops_path_tensor_op_utchmma_src_fp16_dst_fp32_sparsity_off.sum",
+        "sm__ops_path_tensor_op_utchmma_src_fp16_dst_fp32_sparsity_off.sum.per_second",
+        "sm__ops_path_tensor_op_utchmma_src_fp16_dst_fp32_sparsity_off.sum.peak_sustained_elapsed.per_second",
         "smsp__sass_inst_executed_op_utcmma.sum", "smsp__sass_inst_executed_op_tma_ld.sum",
         "smsp__sass_inst_executed_op_tmem_ldt.sum",
         "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed.avg.per_cycle_elapsed",
@@ -33,7 +33,7 @@ KEEP = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
 with open(out, "w") as f:
     f.write(f"# `{cmd}`\n\n{note}\n\nValues per launch.\n\n")
     for r in rows[2:]:
-        f.write(f"## {r[hdr.index('Kernel Name')].split('(')[0]}\n\n| metric | value | unit |\n|---|---|---|\n")
+        f.write(f"## {r[hdr.index('Kernel Name')][:90]}\n\n| metric | value | unit |\n|---|---|---|\n")
         for k in KEEP:
             if k in hdr:
                 i = hdr.index(k)
