@@ -525,8 +525,12 @@ def _run_engine(args, wl):
         alg = 4.0 * nq_k * rows_dom * dim
         exe = (2.0 if f1 else 4.0) * nq_k * rows_dom * dim if dom == "leaf_filter_f16" else 12.0 * nq_k * rows_dom * dim
         op_bytes = (2.0 if f1 else 4.0) * dim if dom == "leaf_filter_f16" else 8.0 * dim  # fp16 operand bytes per row
-        tiles = ((nq_k + 255) // 256) * ((rows_dom + 255) // 256)
-        l2_bytes = tiles * 512 * op_bytes  # every tile pulls 256 query rows + 256 index rows through L2 -> SM
+        # operand bytes through L2 -> SM: the one-product kernels work on half tiles (128 query rows + 256 index rows per
+        # tile, two CTAs per SM), the three-product kernel on 256 + 256 (ncu xbar2l1tex: 20.1 / 12.7 GB at cfg3,
+        # profiles/r02_fused_ncu_full.md -- the rest is the epilogue's ancestor-sum loads)
+        tq = 128 if dom == "leaf_filter_f16" else 256
+        tiles = ((nq_k + tq - 1) // tq) * ((rows_dom + 255) // 256)
+        l2_bytes = tiles * (tq + 256) * op_bytes
         peak = peaks["bf16_tflops"]
         achieved = alg / (ms_dom * 1e-3) / 1e12
         score_ms = stages["internal_scores_f16x3"] + stages["sample_threshold"] + stages["leaf_filter_f16"]

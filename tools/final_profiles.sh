@@ -11,7 +11,7 @@ python bench.py --mode fp32 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/
 python tools/ifit_phases.py 30000 768 unit > gpurun_out/${tag}_ifit_phases.log 2>&1
 python tools/ifit_phases.py 30000 256 whitened >> gpurun_out/${tag}_ifit_phases.log 2>&1
 python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/plain.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${tag}_launches.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/${tag}_launches.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1
 python tools/fused_once.py > gpurun_out/once.log 2>&1 &&
 ncu --set full --import-source on --clock-control none -k regex:"h_score_kernel|h_finish|h_cumsum|hq_build|small_scores|paths_small" -s 12 -c 10 \
