@@ -1,10 +1,12 @@
-"""ifit phase timers (cw_ifit.cu MARK()) for a run: where a level-step spends its time.
-  python tools/ifit_phases.py [n] [d] [kind]"""
+"""ifit phase timers (cw_ifit.cu MARK() / FMARK()) for a run: where a level-step spends its time.
+  python tools/ifit_phases.py [n] [d] [kind] [cluster]"""
 import sys, time
 import numpy as np, torch
 sys.path.insert(0, '.')
-from rag_cobweb_b200 import CobwebTorchTree, synth
+from rag_cobweb_b200 import CobwebTorchTree, synth, _lib
 n, d, kind = int(sys.argv[1]) if len(sys.argv) > 1 else 30000, int(sys.argv[2]) if len(sys.argv) > 2 else 768, sys.argv[3] if len(sys.argv) > 3 else "unit"
+if len(sys.argv) > 4:
+    _lib.check(_lib.load().cw_set_ifit_cluster(int(sys.argv[4])))
 x = torch.from_numpy(synth.corpus(n, d, kind, 0)).cuda()
 t = CobwebTorchTree((d,))
 torch.cuda.synchronize(); t0 = time.time()
@@ -15,3 +17,9 @@ ph = t.store.ifit_phase_cycles()
 tot = sum(ph.values())
 print(f"{n}x{d} {kind}: {n / dt:.0f} inserts/s, {c['levels'] / n:.2f} levels/insert, {dt / c['levels'] * 1e6:.2f} us/level-step, rows/insert {c['rows'] / n:.1f}")
 print("phase share:", {k: round(v / max(tot, 1), 3) for k, v in ph.items()}, "cycles/level", {k: int(v / max(c['levels'], 1)) for k, v in ph.items()})
+base = 16 + 4 * _lib.MAX_CHILDREN + 1 + 3
+w = t.store.scratch[base:base + 48].cpu().numpy().view(np.int64)
+names = {10: "phaseB..entry+list", 11: "cur row load", 12: "slice compute", 13: "slice barrier", 14: "job setup", 15: "child row load",
+         16: "var+log", 17: "terms x2", 18: "team reduce", 19: "sends+more iters", 20: "exchange A", 21: "ranking", 22: "four sums",
+         23: "gchild list wait"}
+print("fine (cycles/level, lead thread 0):", {names[k]: int(w[k] / max(c['levels'], 1)) for k in names})
