@@ -52,6 +52,8 @@ def build(force=False, verbose=False):
     common = [f for f in COMMON if not f.startswith("--use_fast_math")]
     for unit, extra in UNITS:
         obj = os.path.join(CSRC, unit.replace(".cu", ".o"))
+        if unit == "cw_ifit.cu" and os.environ.get("CW_IFIT_FINE_TIMERS"):
+            extra = extra + ["-DCW_IFIT_FINE_TIMERS"]  # per-step timers of the lead thread (tools/ifit_phases.py)
         cmd = [nvcc()] + ARCH + common + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, unit), "-o", obj]
         subprocess.check_call(cmd)
         objs.append(obj)

@@ -92,7 +92,7 @@ def test_ifit_cluster_sizes_agree():
     x, _, ref = build_pair(400, 384, "unit")
     rl, rops, _ = ref.ifit(x, trace=True)
     try:
-        for ncta in (1, 2, 4, 8):
+        for ncta in (1, 2, 4, 8, 16):
             _lib.check(L.cw_set_ifit_cluster(ncta))
             tree = CobwebTorchTree((384,))
             leaves, ops, _ = tree.ifit_batch(x, tag_sentences=True, trace=True)
@@ -101,6 +101,18 @@ def test_ifit_cluster_sizes_agree():
         assert L.cw_set_ifit_cluster(3) != 0
     finally:
         L.cw_set_ifit_cluster(0)
+
+
+def test_ifit_fast_arithmetic_is_ieee():
+    """The branch-free division / logarithm of the ifit scoring jobs give the bits of the IEEE division and of the
+    strict log on 2e8 pseudo-random and edge operands (zero numerators, all-ones mantissas, equal mantissas)."""
+    from rag_cobweb_b200 import _lib
+    L = _lib.load()
+    out = torch.zeros(3, dtype=torch.int64, device="cuda")
+    _lib.check(L.cw_selftest_arith(1 << 18, 800, 12345, out.data_ptr(), _lib.stream_ptr()), "cw_selftest_arith")
+    bad_div, bad_log, tested = out.cpu().tolist()
+    assert tested > 1e8
+    assert bad_div == 0 and bad_log == 0
 
 
 def test_child_pool_compaction_keeps_the_tree():

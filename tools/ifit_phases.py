@@ -20,6 +20,7 @@ print("phase share:", {k: round(v / max(tot, 1), 3) for k, v in ph.items()}, "cy
 base = 16 + 4 * _lib.MAX_CHILDREN + 1 + 3
 w = t.store.scratch[base:base + 48].cpu().numpy().view(np.int64)
 names = {10: "phaseB..entry+list", 11: "cur row load", 12: "slice compute", 13: "slice barrier", 14: "job setup", 15: "child row load",
-         16: "var+log", 17: "terms x2", 18: "team reduce", 19: "sends+more iters", 20: "exchange A", 21: "ranking", 22: "four sums",
+         17: "job arithmetic", 18: "team reduce", 19: "sends+more iters", 20: "exchange A", 21: "ranking", 22: "four sums",
          23: "gchild list wait"}
-print("fine (cycles/level, lead thread 0):", {names[k]: int(w[k] / max(c['levels'], 1)) for k in names})
+if w[10:24].any():
+    print("fine (cycles/level, lead thread 0):", {names[k]: int(w[k] / max(c['levels'], 1)) for k in names})
