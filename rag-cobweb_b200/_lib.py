@@ -20,7 +20,7 @@ IFIT_NODE_SLACK, IFIT_POOL_SLACK = 160, 16384
 H_TILE, H_F1, H_F2 = 256, 1, 2
 FUSED_MAX_K, FUSED_FB_ROUNDS, SMALL_Q, SID_UNRESOLVED, FUSED_STATS, FUSED_STAGES = 30, 2, 32, -2, 12, 7
 
-EXPORTS = ["cw_version", "cw_last_error", "cw_store_init", "cw_ifit", "cw_set_ifit_cluster", "cw_selftest_arith", "cw_categorize_ctas", "cw_categorize",
+EXPORTS = ["cw_version", "cw_last_error", "cw_store_init", "cw_store_derive", "cw_ifit", "cw_set_ifit_cluster", "cw_selftest_arith", "cw_categorize_ctas", "cw_categorize",
            "cw_index_build", "cw_xt_floats", "cw_score_ldq", "cw_dense_node_scores", "cw_topk_chunks", "cw_dense_paths_topk",
            "cw_predict_dense_host", "cw_index_rows_build",
            "cw_h_b_bytes", "cw_h_a_bytes", "cw_h_stages", "cw_h_set_build", "cw_h_rows_isotropic", "cw_fused_predict",
@@ -33,7 +33,8 @@ class CwStore(C.Structure):
                 ("prior_var", C.c_float), ("reserved", C.c_int32),
                 ("mean", C.c_void_p), ("m2", C.c_void_p), ("count", C.c_void_p), ("parent", C.c_void_p),
                 ("child_off", C.c_void_p), ("child_cnt", C.c_void_p), ("child_cap", C.c_void_p),
-                ("child_pool", C.c_void_p), ("n_sent", C.c_void_p), ("free_list", C.c_void_p), ("hdr", C.c_void_p), ("scratch", C.c_void_p)]
+                ("child_pool", C.c_void_p), ("n_sent", C.c_void_p), ("free_list", C.c_void_p), ("hdr", C.c_void_p), ("scratch", C.c_void_p),
+                ("var", C.c_void_p), ("tf", C.c_void_p)]
 
 
 class CwIndex(C.Structure):
@@ -92,6 +93,7 @@ def load():
     L.cw_version.restype = C.c_int
     L.cw_last_error.restype = C.c_char_p
     L.cw_store_init.argtypes = [C.POINTER(CwStore), vp]
+    L.cw_store_derive.argtypes = [C.POINTER(CwStore), C.c_int32, vp]
     L.cw_ifit.argtypes = [C.POINTER(CwStore), vp, i64, vp, vp, vp, i64, i32, vp]
     L.cw_set_ifit_cluster.argtypes = [i32]
     L.cw_selftest_arith.argtypes = [i64, i64, C.c_uint32, vp, vp]

@@ -37,6 +37,7 @@ def broadcast_store(tree, src=0):
                  "free_list"):
         dist.broadcast(getattr(s, name), src)
     s._struct = None
+    s.derive()  # var / tf rows from the received m2 / count
 
 
 class ResultGather:

@@ -34,6 +34,9 @@ class NodeStore:
         new = dict(
             mean=torch.zeros((cap, d), dtype=torch.float32, device=dev),
             m2=torch.zeros((cap, d), dtype=torch.float32, device=dev),
+            # derived rows (compute_var / its log), kept in step with m2 / count by the ifit kernel
+            var=torch.zeros((cap, d), dtype=torch.float32, device=dev),
+            tf=torch.zeros((cap, d), dtype=torch.float32, device=dev),
             count=torch.zeros(cap, dtype=torch.float32, device=dev),
             parent=torch.full((cap,), -2, dtype=torch.int32, device=dev),
             child_off=torch.zeros(cap, dtype=torch.int32, device=dev),
@@ -45,7 +48,7 @@ class NodeStore:
         )
         if self.cap:
             n = self.cap
-            for k in ("mean", "m2", "count", "parent", "child_off", "child_cnt", "child_cap", "n_sent", "free_list"):
+            for k in ("mean", "m2", "var", "tf", "count", "parent", "child_off", "child_cnt", "child_cap", "n_sent", "free_list"):
                 new[k][:n] = getattr(self, k)
             new["child_pool"][: self.pool_cap] = self.child_pool
         else:
@@ -61,7 +64,7 @@ class NodeStore:
             s = _lib.CwStore()
             s.D, s.cap, s.pool_cap, s.flags, s.prior_var = self.d, self.cap, self.pool_cap, self.flags, self.prior_var
             for k in ("mean", "m2", "count", "parent", "child_off", "child_cnt", "child_cap", "child_pool", "n_sent",
-                      "free_list", "hdr", "scratch"):
+                      "free_list", "hdr", "scratch", "var", "tf"):
                 setattr(s, k, getattr(self, k).data_ptr())
             self._struct = s
         return C.byref(self._struct)
@@ -186,8 +189,14 @@ class NodeStore:
         hdr[_lib.HDR_ROOT], hdr[_lib.HDR_N_USED], hdr[_lib.HDR_POOL_USED] = 0, n, int(capn.sum())
         hdr[_lib.HDR_MAX_CHILD] = int(cnt.max()) if n else 0
         self.hdr.copy_(torch.as_tensor(hdr, device=dev))
+        self.derive(n)
+
+    def derive(self, n=None):
+        """Rebuild the derived rows (var, tf) of node rows [0, n) after mean / m2 / count were written from outside."""
+        n = int(self.header()[_lib.HDR_N_USED]) if n is None else int(n)
+        _lib.check(_lib.load().cw_store_derive(self.struct(), n, _lib.stream_ptr()), "cw_store_derive")
 
     def bytes(self):
         return sum(getattr(self, k).numel() * getattr(self, k).element_size()
-                   for k in ("mean", "m2", "count", "parent", "child_off", "child_cnt", "child_cap", "child_pool",
+                   for k in ("mean", "m2", "var", "tf", "count", "parent", "child_off", "child_cnt", "child_cap", "child_pool",
                              "n_sent", "free_list"))

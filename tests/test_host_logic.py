@@ -146,7 +146,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name)
     assert lib.cw_version() == 100
-    assert ctypes.sizeof(_lib.CwStore) == 24 + 12 * 8
+    assert ctypes.sizeof(_lib.CwStore) == 24 + 14 * 8
     assert lib.cw_topk_chunks(1025) == 3 and lib.cw_xt_floats(129, 20) == 2 * 2 * 16 * 128  # 2 chunks + the threshold slot
     # fp16 operand sets: layout F1 = 32 attributes per slab, F2 = 16; one-product sets pack two slabs into a stage
     assert lib.cw_h_stages(768, _lib.H_F1, 1) == 12 and lib.cw_h_stages(768, _lib.H_F2, 3) == 48 and lib.cw_h_stages(33, _lib.H_F1, 1) == 1
