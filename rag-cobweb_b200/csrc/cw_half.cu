@@ -88,29 +88,10 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
-// the same copy delivered to the same shared-memory offset of every CTA in ctaMask, each one's mbarrier counting the bytes
-__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint16_t mask) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar), "h"(mask)
-                 : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_rank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// ... arriving on the barrier at the same offset in every CTA of ctaMask
-__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
-                 : "memory");
 }
 // D[tmem] (+)= A[smem] * B[smem]^T, one 128 x 256 x 16 fp16 MMA, fp32 accumulate
 __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -236,12 +217,7 @@ struct KCfg {
 };
 static_assert(KCfg<true>::SMEM * 2 + 2048 <= 227 * 1024 + 1024, "two half-tile CTAs per SM");
 
-// PAIR (half tiles only): the CTAs 2c, 2c+1 form a cluster and take the same row tile with neighbouring query tiles (the
-// tile order already puts them side by side).  Each loads one of the two row-operand images of a stage and multicasts it
-// into both CTAs' shared memory, so the row operands cross the L2 -> SM path once per pair instead of once per CTA: a third
-// less operand traffic for the one-product kernels, whose MMA phase that path bounds.  A stage is free when BOTH CTAs'
-// MMAs have read it (the commit arrives on both empty barriers).
-template <int NPROD, int MODE, bool HALF, bool PAIR>
+template <int NPROD, int MODE, bool HALF>
 __global__ void __launch_bounds__(KCfg<HALF>::THR, KCfg<HALF>::CTAS)
 h_score_kernel(const unsigned char *__restrict__ A, const unsigned char *__restrict__ B, const HEpi epi, int n_qtiles,
                int nt_begin, int n_ntiles, int n_stages, int pq) {
@@ -261,7 +237,7 @@ h_score_kernel(const unsigned char *__restrict__ A, const unsigned char *__restr
     if (threadIdx.x == 0) {
         for (int s = 0; s < K::NST; s++) {
             mbar_init(full0 + 8 * s, 1);
-            mbar_init(empty0 + 8 * s, PAIR ? 2 : 1);
+            mbar_init(empty0 + 8 * s, 1);
         }
         mbar_init(accf, 1);
         mbar_init(acce, K::EPIW);  // one arrival per epilogue warp
@@ -272,8 +248,7 @@ h_score_kernel(const unsigned char *__restrict__ A, const unsigned char *__restr
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
-    if (PAIR) cluster_sync_all();  // the peer's barriers exist before anything is multicast at them
-    else __syncthreads();
+    __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
     const long long n_tiles = (long long)n_qtiles * n_ntiles;
@@ -299,12 +274,7 @@ h_score_kernel(const unsigned char *__restrict__ A, const unsigned char *__restr
                     } else {
                         bulk_g2s(sb, asrc + (size_t)s * SIDE, SIDE, full0 + 8 * stage);
                     }
-                    if (PAIR) {
-                        const uint32_t r = cluster_rank();
-                        bulk_g2s_mc(sb + K::A_SIDE + r * IMG, bsrc + (size_t)s * SIDE + (size_t)r * IMG, IMG, full0 + 8 * stage, (uint16_t)3);
-                    } else {
-                        bulk_g2s(sb + K::A_SIDE, bsrc + (size_t)s * SIDE, SIDE, full0 + 8 * stage);
-                    }
+                    bulk_g2s(sb + K::A_SIDE, bsrc + (size_t)s * SIDE, SIDE, full0 + 8 * stage);
                     if (++stage == K::NST) { stage = 0; phase ^= 1; }
                 }
             }
@@ -356,8 +326,7 @@ h_score_kernel(const unsigned char *__restrict__ A, const unsigned char *__restr
                             }
                         }
                     }
-                    if (PAIR) tc_commit_mc(empty0 + 8 * stage, (uint16_t)3);  // ... in both CTAs of the pair
-                    else tc_commit(empty0 + 8 * stage);  // stage free once these MMAs have read it
+                    tc_commit(empty0 + 8 * stage);  // stage free once these MMAs have read it
                     if (s == n_stages - 1) tc_commit(accf);
                     if (++stage == K::NST) { stage = 0; phase ^= 1; }
                 }
@@ -554,8 +523,7 @@ h_score_kernel(const unsigned char *__restrict__ A, const unsigned char *__restr
     }
 
     tc_fence_before();
-    if (PAIR) cluster_sync_all();  // no CTA leaves while its peer may still multicast into it or arrive on its barriers
-    else __syncthreads();
+    __syncthreads();
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(K::TMEM_COLS) : "memory");
@@ -1226,62 +1194,34 @@ extern "C" int cw_h_rows_isotropic(const cw_store *s, const int32_t *order, cons
     return out;
 }
 
-template <int NPROD, int MODE, bool HALF, bool PAIR>
+template <int NPROD, int MODE, bool HALF>
 static int h_launch_t(const cw_h_set *hs, const void *A, int64_t nq, int nt_begin, int nt_count, const HEpi &epi, cudaStream_t st) {
     using K = KCfg<HALF>;
-    int n_qtiles = (int)((nq + K::TQK - 1) / K::TQK);
-    if (PAIR) n_qtiles = (n_qtiles + 1) & ~1;  // pairs of query tiles (a tile of pure padding is skipped by the epilogue)
-    auto kern = h_score_kernel<NPROD, MODE, HALF, PAIR>;
+    const int n_qtiles = (int)((nq + K::TQK - 1) / K::TQK);
+    auto kern = h_score_kernel<NPROD, MODE, HALF>;
     int rc = cw_check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM), "cw_h: smem attribute");
     if (rc) return rc;
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long n_tiles = (long long)n_qtiles * nt_count;
     if (n_tiles == 0) return 0;
-    int grid = (int)(n_tiles < (long long)sms * K::CTAS ? n_tiles : sms * K::CTAS);
-    if (PAIR) grid &= ~1;
+    const int grid = (int)(n_tiles < (long long)sms * K::CTAS ? n_tiles : sms * K::CTAS);
     // query-tile panels: the panel's query operands should sit in L2 (~40 MB of it) while the row operands stream
     const long long a_tile = (long long)hs->n_stages * K::A_SIDE;
     int pq_max = (int)((40ll << 20) / a_tile);
     if (pq_max < 1) pq_max = 1;
     const int n_panels = (n_qtiles + pq_max - 1) / pq_max;
-    int pq = (n_qtiles + n_panels - 1) / n_panels;
-    if (PAIR) pq = (pq + 1) & ~1;  // even panels keep the tiles 2c, 2c+1 on one row tile
-    if (!PAIR) {
-        kern<<<grid, K::THR, K::SMEM, st>>>(reinterpret_cast<const unsigned char *>(A), reinterpret_cast<const unsigned char *>(hs->B),
-                                            epi, n_qtiles, nt_begin, nt_count, hs->n_stages, pq);
-    } else {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(grid);
-        cfg.blockDim = dim3(K::THR);
-        cfg.dynamicSmemBytes = K::SMEM;
-        cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        rc = cw_check_cuda(cudaLaunchKernelEx(&cfg, kern, reinterpret_cast<const unsigned char *>(A),
-                                              reinterpret_cast<const unsigned char *>(hs->B), epi, n_qtiles, nt_begin, nt_count,
-                                              (int)hs->n_stages, pq),
-                           "cw_h: paired score kernel");
-        if (rc) return rc;
-    }
+    const int pq = (n_qtiles + n_panels - 1) / n_panels;
+    kern<<<grid, K::THR, K::SMEM, st>>>(reinterpret_cast<const unsigned char *>(A), reinterpret_cast<const unsigned char *>(hs->B),
+                                        epi, n_qtiles, nt_begin, nt_count, hs->n_stages, pq);
     return cw_check_cuda(cudaGetLastError(), "cw_h: score kernel");
 }
-// the one-product kernels take half tiles (two CTAs per SM), in multicast pairs, unless COBWEB_B200_FULL_TILE=1 asks for the
-// full ones or COBWEB_B200_NO_PAIR=1 for unpaired half tiles
+// the one-product kernels take half tiles (two CTAs per SM) unless COBWEB_B200_FULL_TILE=1 asks for the full ones
 template <int NPROD, int MODE>
 static int h_launch(const cw_h_set *hs, const void *A, int64_t nq, int nt_begin, int nt_count, const HEpi &epi, cudaStream_t st) {
     static const bool full_tile = getenv("COBWEB_B200_FULL_TILE") && atoi(getenv("COBWEB_B200_FULL_TILE")) != 0;
-    static const bool no_pair = getenv("COBWEB_B200_NO_PAIR") && atoi(getenv("COBWEB_B200_NO_PAIR")) != 0;
-    if (NPROD == 1 && !full_tile) {
-        if (!no_pair) return h_launch_t<NPROD, MODE, true, true>(hs, A, nq, nt_begin, nt_count, epi, st);
-        return h_launch_t<NPROD, MODE, true, false>(hs, A, nq, nt_begin, nt_count, epi, st);
-    }
-    return h_launch_t<NPROD, MODE, false, false>(hs, A, nq, nt_begin, nt_count, epi, st);
+    if (NPROD == 1 && !full_tile) return h_launch_t<NPROD, MODE, true>(hs, A, nq, nt_begin, nt_count, epi, st);
+    return h_launch_t<NPROD, MODE, false>(hs, A, nq, nt_begin, nt_count, epi, st);
 }
 
 int cw_small_predict_impl(const cw_index *ix, const float *Q, int64_t nq, const int32_t *which, const int32_t *n_dev,
