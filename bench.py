@@ -542,10 +542,9 @@ def _run_engine(args, wl):
             "flops_per_launch": alg, "executed_flops_per_launch": exe, "executed_tflops": exe / (ms_dom * 1e-3) / 1e12,
             "executed_frac": exe / (ms_dom * 1e-3) / 1e12 / peak,
             "l2_to_sm_bytes_per_launch": l2_bytes, "l2_to_sm_tb_s": l2_bytes / (ms_dom * 1e-3) / 1e12,
-            "bound_note": "the filter is bound by its epilogue, not by operands: multicasting the row operands across CTA pairs "
-                          "(a third less L2->SM traffic) left it at 1.92 ms, one half-tile CTA per SM takes 2.93 ms (27k cycles "
-                          "per tile, 8.8k of them MMAs), ncu counts 31 instructions per (query, row) pair of which 5 are the "
-                          "arithmetic (DESIGN.md section 5, Bounds)",
+            "bound_note": "two limits together (DESIGN.md section 5, Bounds): operand ingest per SM -- with the epilogue's "
+                          "arithmetic compiled out the kernel takes 1.45 ms = 12.5 TB/s L2->SM = 44 B/clk per SM -- and a drain "
+                          "of the accumulator that overlaps the other CTA's MMAs only partly (one half-tile CTA per SM: 2.93 ms)",
             "peak_source": f"kind::f16 dense = the bf16 burst peak, {peak_src}",
             "note": "achieved = ALGORITHMIC flops of the dominant kernel's rows (4 per query, row and attribute: the "
                     "reference's direct form) / its CUDA-event time; executed_* = what the tensor pipe really does. The "
