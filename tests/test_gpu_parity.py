@@ -115,6 +115,30 @@ def test_ifit_fast_arithmetic_is_ieee():
     assert bad_div == 0 and bad_log == 0
 
 
+def test_derived_rows_follow_the_statistics():
+    """cw_store.var / .tf (compute_var and its log, cached per node) are what the ifit kernel scores children from.  After
+    every kind of update (increment, new, merge, split, fringe split, duplicates) they equal a fresh derivation from
+    (m2, count) bit for bit, for every live node and every scoring mode; a tree reloaded from its arrays (derived rows
+    rebuilt by cw_store_derive) keeps growing exactly like the oracle's."""
+    for kw in (dict(), dict(use_kl=False), dict(use_info=False), dict(acuity_cutoff=True)):
+        x, tree, ref = build_pair(700, 96, "whitened", dups=True, **kw)
+        tree.ifit_batch(x[:400], tag_sentences=True)
+        st = tree.store
+        n_used = int(st.header()[1])
+        live = (st.parent[:n_used] > -2) & (st.count[:n_used] > 0)
+        var_k, tf_k = st.var[:n_used].clone(), st.tf[:n_used].clone()
+        st.derive(n_used)
+        assert torch.equal(st.var[:n_used][live], var_k[live]) and torch.equal(st.tf[:n_used][live], tf_k[live]), kw
+        # the same tree rebuilt from its arrays (what load_json / load_snapshot do), then 300 more inserts
+        b = tree.bfs()
+        mean, m2 = st.rows(b["order"])
+        tree2 = CobwebTorchTree((96,), **kw)
+        tree2.load_arrays(b["parent"], b["count"], b["nsent"], mean, m2)
+        leaves2 = tree2.ifit_batch(x[400:], tag_sentences=True)
+        rl = ref.ifit(x)
+        assert_same_tree(tree2, ref, leaves2.cpu().numpy(), rl[400:])
+
+
 def test_child_pool_compaction_keeps_the_tree():
     """Child lists are rewritten contiguously (leaked chunks dropped) without changing the tree, and
     inserts continue bit-exactly afterwards."""
