@@ -139,6 +139,27 @@ def test_derived_rows_follow_the_statistics():
         assert_same_tree(tree2, ref, leaves2.cpu().numpy(), rl[400:])
 
 
+def test_ifit_is_deterministic_under_repetition():
+    """The cluster protocol of cw_ifit (scores through distributed shared memory, CTAs running phases ahead of each other)
+    must not let timing into the result: the same stream gives the same decision trace every time, for every cluster
+    size, on shapes with one-warp and multi-warp teams and with many rounds per phase (high fan-out)."""
+    from rag_cobweb_b200 import _lib
+    L = _lib.load()
+    try:
+        for n, d, kind in ((4000, 128, "unit"), (3000, 768, "unit"), (4000, 256, "whitened")):
+            x = torch.from_numpy(synth.corpus(n, d, kind, seed=3)).cuda()
+            want = None
+            for rep, ncta in enumerate((0, 0, 0, 8, 16, 4, 0)):
+                _lib.check(L.cw_set_ifit_cluster(ncta))
+                tree = CobwebTorchTree((d,))
+                _, ops, off = tree.ifit_batch(x, tag_sentences=True, trace=True)
+                if want is None:
+                    want = (ops, off)
+                assert np.array_equal(ops, want[0]) and np.array_equal(off, want[1]), (n, d, kind, rep, ncta)
+    finally:
+        L.cw_set_ifit_cluster(0)
+
+
 def test_child_pool_compaction_keeps_the_tree():
     """Child lists are rewritten contiguously (leaked chunks dropped) without changing the tree, and
     inserts continue bit-exactly afterwards."""
