@@ -19,8 +19,8 @@ print(f"{n}x{d} {kind}: {n / dt:.0f} inserts/s, {c['levels'] / n:.2f} levels/ins
 print("phase share:", {k: round(v / max(tot, 1), 3) for k, v in ph.items()}, "cycles/level", {k: int(v / max(c['levels'], 1)) for k, v in ph.items()})
 base = 16 + 4 * _lib.MAX_CHILDREN + 1 + 3
 w = t.store.scratch[base:base + 48].cpu().numpy().view(np.int64)
-names = {10: "phaseB..entry+list", 11: "cur row load", 12: "slice compute", 13: "slice barrier", 14: "job setup", 15: "child row load",
-         17: "job arithmetic", 18: "team reduce", 19: "sends+more iters", 20: "exchange A", 21: "ranking", 22: "four sums",
-         23: "gchild list wait"}
+names = {10: "phase B .. next entry", 11: "current node row load", 12: "slice work (this team: the cached rows)", 13: "wait for the P' slices", 14: "job setup", 15: "child row load",
+         17: "job arithmetic", 18: "team reduce", 19: "sends + further rounds", 20: "exchange A", 21: "-", 22: "-",
+         23: "decision A + best1 child list (waiting)"}
 if w[10:24].any():
-    print("fine (cycles/level, lead thread 0):", {names[k]: int(w[k] / max(c['levels'], 1)) for k in names})
+    print("fine (cycles/level, first thread of the team with job 0 in the lead CTA):", {names[k]: int(w[k] / max(c['levels'], 1)) for k in names})
