@@ -88,7 +88,9 @@ class NodeStore:
                     levels=self._u64(h, _lib.HDR_N_LEVELS))
 
     def ifit_phase_cycles(self):
-        """Cycles the lead CTA spent per ifit phase since the store was created (cw_ifit.cu MARK())."""
+        """Cycles the lead CTA spent per ifit phase since the store was created (cw_ifit.cu MARK()).  All zero unless the
+        library was built with the timers (`CW_IFIT_FINE_TIMERS=1 python rag-cobweb_b200/build.py --force`): they sit on
+        the critical path of every level-step and cost ~2 % of the insert rate."""
         base = 16 + 4 * _lib.MAX_CHILDREN + 1 + 3
         w = self.scratch[base:base + 20].cpu().numpy().view(np.int64)
         names = ["apply", "S1", "lists+slices", "phaseA", "S2", "decA", "phaseB", "S3", "decB", "-"]

@@ -12,4 +12,4 @@ for ncta in [int(v) for v in sys.argv[4:]]:
     t.ifit_batch(x, tag_sentences=True)
     torch.cuda.synchronize(); dt = time.time() - t0
     c = t.store.counters(); ph = t.store.ifit_phase_cycles(); tot = sum(ph.values())
-    print(f"ncta={ncta}: {n/dt:.0f} inserts/s, {dt/c['levels']*1e6:.1f} us/level, rows/insert {c['rows']/n:.0f}", {k: round(100*v/tot) for k, v in ph.items() if v})
+    print(f"ncta={ncta}: {n/dt:.0f} inserts/s, {dt/c['levels']*1e6:.1f} us/level, rows/insert {c['rows']/n:.0f}", {k: round(100*v/max(tot,1)) for k, v in ph.items() if v})

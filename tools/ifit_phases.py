@@ -16,6 +16,8 @@ c = t.store.counters()
 ph = t.store.ifit_phase_cycles()
 tot = sum(ph.values())
 print(f"{n}x{d} {kind}: {n / dt:.0f} inserts/s, {c['levels'] / n:.2f} levels/insert, {dt / c['levels'] * 1e6:.2f} us/level-step, rows/insert {c['rows'] / n:.1f}")
+if tot == 0:
+    print("(phase timers not compiled in: CW_IFIT_FINE_TIMERS=1 python rag-cobweb_b200/build.py --force)")
 print("phase share:", {k: round(v / max(tot, 1), 3) for k, v in ph.items()}, "cycles/level", {k: int(v / max(c['levels'], 1)) for k, v in ph.items()})
 base = 16 + 4 * _lib.MAX_CHILDREN + 1 + 3
 w = t.store.scratch[base:base + 48].cpu().numpy().view(np.int64)
